@@ -1,0 +1,181 @@
+"""Drop-in for reference ``util/mesh.py`` (class ``Mesh``) — the graph / static-geometry builder of the hot path.
+
+Same constructor (``Mesh(path, build_mat=False)``) and the same attributes the training path reads
+(``vs, faces, fn, fa, fc, vn, edges, f2f, f_edges, v2v_mat, v_dims, vf``), but built with sorted
+array passes instead of per-face Python dict/set/Counter loops (reference util/mesh.py:45-85,152-197 is
+~0.1 ms/face; this is ~1 µs/face).
+
+Bit-exactness contract (SURVEY.md §7 hard part 5): integer outputs are identical to the reference in canonical
+form —
+  * ``edges``   : identical array, identical order (first appearance scanning faces; reference :54-72,82);
+  * ``f2f``     : identical as a set per row. The reference's per-row order comes from CPython ``set``
+                  iteration (:176-186) and is not defined; here each row is ascending with the -1 padding last;
+  * ``f_edges`` : identical as a multiset of directed pairs, grouped by source face like the reference;
+  * ``v_dims``  : identical values; ``v2v_mat`` identical COO (edges then flipped edges, uncoalesced; :189-197);
+  * float64 geometry (``fn, fa, fc, vn``) uses the same numpy expressions as the reference (:87-112).
+Only manifold meshes are supported, like the reference (a third face on an edge raises there at :75-76; here it
+raises ``ValueError``).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+
+class Mesh:
+    def __init__(self, path=None, build_mat: bool = False, *, vs=None, faces=None):
+        self.path = path
+        if path is not None:
+            self.vs, self.faces = self.fill_from_file(path)
+        else:  # in-memory construction (synthetic meshes; no OBJ round trip)
+            self.vs = np.ascontiguousarray(vs, dtype=np.float64)
+            self.faces = np.ascontiguousarray(faces, dtype=np.int64)
+            assert self.faces.ndim == 2 and self.faces.shape[1] == 3
+            assert np.logical_and(self.faces >= 0, self.faces < len(self.vs)).all()
+        self.compute_face_normals()
+        self.compute_face_center()
+        self.device = "cpu"
+        self.build_gemm()
+        self.compute_vert_normals()
+        self.build_v2v()
+        self.build_vf()
+        if build_mat:
+            raise NotImplementedError(
+                "build_uni_lap / build_mesh_lap are never called by the reference drivers (out of scope, "
+                "SURVEY.md §2.1 row 4)")
+
+    # ---- OBJ ingest (reference util/mesh.py:23-43) -----------------------------------------------------
+    def fill_from_file(self, path):
+        vs, faces = [], []
+        with open(path) as f:
+            for line in f:
+                sp = line.split()
+                if not sp:
+                    continue
+                if sp[0] == "v":
+                    vs.append((float(sp[1]), float(sp[2]), float(sp[3])))
+                elif sp[0] == "f":
+                    ids = [int(c.split("/")[0]) for c in sp[1:]]
+                    assert len(ids) == 3
+                    nv = len(vs)
+                    faces.append([(i - 1) if i >= 0 else (nv + i) for i in ids])
+        vs = np.asarray(vs, dtype=np.float64).reshape(-1, 3)
+        faces = np.asarray(faces, dtype=int).reshape(-1, 3)
+        assert np.logical_and(faces >= 0, faces < len(vs)).all()
+        return vs, faces
+
+    # ---- edges (reference build_gemm :45-85, edges part only) --------------------------------------------
+    def build_gemm(self):
+        faces = self.faces
+        nv = len(self.vs)
+        he = np.stack([faces[:, [0, 1]], faces[:, [1, 2]], faces[:, [2, 0]]], axis=1).reshape(-1, 2)
+        he = np.sort(he, axis=1).astype(np.int64)
+        key = he[:, 0] * np.int64(nv) + he[:, 1]
+        uniq, first, inv, cnt = np.unique(key, return_index=True, return_inverse=True, return_counts=True)
+        if cnt.size and cnt.max() > 2:
+            raise ValueError("non-manifold mesh: an edge is shared by more than two faces")
+        order = np.argsort(first, kind="stable")           # first-appearance order
+        rank = np.empty_like(order)
+        rank[order] = np.arange(order.size)
+        self.edges = he[first[order]].astype(np.int32)
+        self.edges_count = int(order.size)
+        # half-edge slot (3*f + k) -> edge id in first-appearance numbering
+        self.face_edges = rank[inv.reshape(-1)].reshape(-1, 3)
+
+    # ---- float64 static geometry: same expressions as the reference (:87-112) -----------------------------
+    def compute_face_normals(self):
+        face_normals = np.cross(self.vs[self.faces[:, 1]] - self.vs[self.faces[:, 0]],
+                                self.vs[self.faces[:, 2]] - self.vs[self.faces[:, 0]])
+        norm = np.linalg.norm(face_normals, axis=1, keepdims=True) + 1e-24
+        face_areas = 0.5 * np.sqrt((face_normals ** 2).sum(axis=1))
+        face_normals /= norm
+        self.fn, self.fa = face_normals, face_areas
+
+    def compute_vert_normals(self):
+        nv = len(self.vs)
+        vn = np.zeros((nv, 3), dtype=np.float64)
+        idx = self.faces.reshape(-1)
+        rep = np.repeat(self.fn, 3, axis=0)
+        for c in range(3):
+            vn[:, c] = np.bincount(idx, weights=rep[:, c], minlength=nv)
+        nrm = np.sqrt((vn * vn).sum(axis=1, keepdims=True))
+        nrm[nrm == 0.0] = 1.0
+        self.vn = vn / nrm
+
+    def compute_face_center(self):
+        self.fc = np.sum(self.vs[self.faces], 1) / 3.0
+
+    # ---- vertex adjacency (reference build_v2v :189-197) ------------------------------------------------
+    def build_v2v(self):
+        v2v_inds = self.edges.T
+        v2v_inds = torch.from_numpy(np.concatenate([v2v_inds, v2v_inds[[1, 0]]], axis=1)).long()
+        v2v_vals = torch.ones(v2v_inds.shape[1]).float()
+        nv = len(self.vs)
+        self.v2v_mat = torch.sparse_coo_tensor(v2v_inds, v2v_vals, size=(nv, nv))
+        self.v_dims = torch.from_numpy(
+            np.bincount(self.edges.reshape(-1).astype(np.int64), minlength=nv).astype(np.float32))
+
+    # ---- vertex->faces and face adjacency (reference build_vf :152-187) -----------------------------------
+    def build_vf(self):
+        faces = self.faces
+        nf, nv = len(faces), len(self.vs)
+        # v->f CSR: incident faces of each vertex, ascending face id
+        flat_v = faces.reshape(-1)
+        flat_f = np.repeat(np.arange(nf, dtype=np.int64), 3)
+        order = np.lexsort((flat_f, flat_v))
+        sv, sf = flat_v[order], flat_f[order]
+        if sv.size:
+            keep = np.ones(sv.size, dtype=bool)
+            keep[1:] = (sv[1:] != sv[:-1]) | (sf[1:] != sf[:-1])   # a degenerate face lists a vertex twice
+            sv, sf = sv[keep], sf[keep]
+        self.vf_ptr = np.zeros(nv + 1, dtype=np.int64)
+        np.cumsum(np.bincount(sv, minlength=nv), out=self.vf_ptr[1:])
+        self.vf_idx = sf
+        self._vf = None
+
+        # face adjacency through shared edges: an edge with two faces makes them neighbours
+        fe = self.face_edges.reshape(-1)
+        half = np.arange(3 * nf, dtype=np.int64)
+        o = np.argsort(fe, kind="stable")
+        fe_s, half_s = fe[o], half[o]
+        pair = np.nonzero(fe_s[1:] == fe_s[:-1])[0]
+        fa_, fb_ = half_s[pair] // 3, half_s[pair + 1] // 3
+        ok = fa_ != fb_
+        fa_, fb_ = fa_[ok], fb_[ok]
+        src = np.concatenate([fa_, fb_])
+        dst = np.concatenate([fb_, fa_])
+        # unique directed pairs (two faces sharing two edges would otherwise repeat; the reference's Counter
+        # keys are unique too)
+        pk = np.unique(src * np.int64(nf) + dst)
+        src, dst = pk // nf, pk % nf
+        deg = np.bincount(src, minlength=nf)
+        if deg.size and deg.max() > 3:
+            raise ValueError("non-manifold mesh: a face has more than three edge neighbours")
+        ptr = np.zeros(nf + 1, dtype=np.int64)
+        np.cumsum(deg, out=ptr[1:])
+        f2f = -np.ones((nf, 3), dtype=np.int64)
+        slot = np.arange(src.size, dtype=np.int64) - ptr[src]
+        f2f[src, slot] = dst
+        self.f2f = f2f
+        self.f_edges = np.stack([src, dst]).astype(np.int64)
+
+    @property
+    def vf(self):
+        """list of ``set`` per vertex like the reference (:153-158). Built lazily: only
+        ``models.vertex_updating`` and the numpy ``bnf`` read it, never the training step."""
+        if self._vf is None:
+            p, idx = self.vf_ptr, self.vf_idx
+            self._vf = [set(idx[p[i]:p[i + 1]].tolist()) for i in range(len(self.vs))]
+        return self._vf
+
+    @property
+    def v2f_mat(self):
+        rows = np.repeat(np.arange(len(self.vs), dtype=np.int64), np.diff(self.vf_ptr))
+        inds = torch.from_numpy(np.stack([rows, self.vf_idx]))
+        return torch.sparse_coo_tensor(inds, torch.ones(inds.shape[1]), size=(len(self.vs), len(self.faces)))
+
+    # ---- writers (reference :267-285) -------------------------------------------------------------------
+    def save(self, filename):
+        assert len(self.vs) > 0
+        from ..synth import write_obj
+        write_obj(filename, self.vs, self.faces)

@@ -1,0 +1,74 @@
+"""The product's vectorised ``Mesh`` (dual_dmp_b200/util/mesh.py) is bit-exact, in canonical form, against the REAL
+reference's outputs (tests/golden) and against the loop oracle on other meshes; edge cases of the reference."""
+import os
+
+import numpy as np
+import pytest
+
+from dual_dmp_b200 import synth
+from dual_dmp_b200.util.mesh import Mesh
+from oracle.mesh_ref import MeshRef, canonical_f2f, canonical_pairs
+
+CASES = ["ico3", "ico6", "open4", "tetra", "strip2"]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_against_reference_golden(golden_dir, name):
+    g = dict(np.load(os.path.join(golden_dir, name + ".npz")))
+    m = Mesh(vs=g["vs"], faces=g["faces"])
+    assert np.array_equal(m.edges, g["edges"]) and m.edges.dtype == np.int32
+    assert np.array_equal(canonical_f2f(m.f2f), g["f2f_canon"]) and m.f2f.dtype == np.int64
+    assert np.array_equal(m.f2f, g["f2f_canon"])          # the product emits the canonical form directly
+    assert np.array_equal(canonical_pairs(m.f_edges), g["f_edges_canon"])
+    assert np.array_equal(m.v_dims.numpy(), g["v_dims"])
+    for k in ("fn", "fa", "fc"):
+        assert np.array_equal(getattr(m, k), g[k]), k
+    assert np.allclose(m.vn, g["vn"], rtol=0, atol=1e-15)
+    v2v = m.v2v_mat
+    assert v2v._nnz() == 2 * len(g["edges"])
+    assert np.array_equal(v2v._indices()[:, :len(g["edges"])].numpy(), g["edges"].T.astype(np.int64))
+
+
+@pytest.mark.parametrize("maker", [lambda: synth.icosphere(9), lambda: synth.open_patch(7, 0.2),
+                                   lambda: synth.open_patch(5, -0.3)])
+def test_against_loop_oracle(maker):
+    vs, faces = maker()
+    rng = np.random.RandomState(0)
+    perm = rng.permutation(len(faces))                     # shuffled face order exercises first-appearance logic
+    faces = faces[perm]
+    m, r = Mesh(vs=vs, faces=faces), MeshRef(vs, faces)
+    assert np.array_equal(m.edges, r.edges)
+    assert np.array_equal(m.f2f, r.f2f)
+    assert np.array_equal(canonical_pairs(m.f_edges), canonical_pairs(r.f_edges))
+    assert np.array_equal(m.v_dims.numpy(), r.v_dims)
+    assert [sorted(s) for s in m.vf] == [sorted(s) for s in r.vf]
+
+
+def test_obj_round_trip(tmp_path):
+    vs, faces = synth.icosphere(2)
+    p = tmp_path / "a.obj"
+    synth.write_obj(str(p), vs, faces)
+    m = Mesh(str(p))
+    assert np.array_equal(m.faces, faces)
+    assert np.allclose(m.vs, vs.astype(np.float32), atol=1e-8)
+    m.save(str(tmp_path / "b.obj"))
+    m2 = Mesh(str(tmp_path / "b.obj"))
+    assert np.array_equal(m2.vs, m.vs)
+
+
+def test_non_manifold_raises():
+    vs = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1], [0, -1, 0]], dtype=np.float64)
+    faces = np.array([[0, 1, 2], [0, 1, 3], [0, 1, 4]])    # three faces on edge (0,1); reference: IndexError
+    with pytest.raises(ValueError):
+        Mesh(vs=vs, faces=faces)
+
+
+def test_icosphere_invariants():
+    vs, faces = synth.icosphere(5)
+    m = Mesh(vs=vs, faces=faces)
+    deg = m.v_dims.numpy()
+    assert (deg == 5).sum() == 12 and (deg == 6).sum() == len(vs) - 12
+    assert (m.f2f >= 0).all()
+    assert m.f_edges.shape == (2, 3 * len(faces))
+    fwd = set(map(tuple, m.f_edges.T.tolist()))
+    assert fwd == set((b, a) for a, b in fwd) and len(fwd) == m.f_edges.shape[1]
