@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""Benchmark of the Dual-DMP training hot path (BASELINE.json metric: train iters/s of the dual GCN step —
+PosNet + NormalNet forward, five losses, backward, clip, Adam; reference main.py:88-110 — at 1M faces).
+
+  python bench.py --gpus N --steps K --warmup W            our arm   (libddmp_b200 CUDA kernels)
+  python bench.py --impl reference --gpus N ...            reference arm: the CPU oracle port of the reference's
+                                                           PyG path on the host cores, on a bounded sample
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "train iters/s (dual GCN fwd+bwd+loss+clip+Adam)"
+WIDTHS_POS = [16, 32, 64, 128, 256, 256, 512, 512, 256, 256, 128, 64, 32]
+WIDTHS_NORM = [7, 32, 64, 128, 256, 256, 512, 512, 256, 256, 128, 64, 32]
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=224, help="icosphere frequency: F = 20 n^2 (224 -> 1,003,520 faces)")
+    ap.add_argument("--bnfloop", type=int, default=1)
+    ap.add_argument("--k", type=float, nargs=5, default=[3.0, 4.0, 4.0, 4.0, 1.0])
+    ap.add_argument("--cpu-n", type=int, default=40, help="icosphere frequency of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--detail", default=None, help="write a per-kernel-group timing table (JSON) to this path")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def build_case(n):
+    from dual_dmp_b200 import synth
+    from dual_dmp_b200.util.datamaker import dataset_from_meshes
+    from dual_dmp_b200.util.mesh import Mesh
+    case = synth.make_case(n)
+    n_mesh = Mesh(vs=case.noise_vs, faces=case.faces)
+    s_mesh = Mesh(vs=case.smooth_vs, faces=case.faces)
+    return n_mesh, s_mesh, dataset_from_meshes(n_mesh, s_mesh)
+
+
+def spmm_bytes(n_nodes, nnz, C):
+    """rowptr + col + w + read H once + write Y once."""
+    return 4 * ((n_nodes + 1) + 2 * nnz + 2 * n_nodes * C)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for i, nm in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    assert torch.cuda.is_available(), "bench.py (our arm) needs a CUDA device; there is no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    from dual_dmp_b200 import functional as F_
+    from dual_dmp_b200._lib import lib
+    from dual_dmp_b200.util import loss as L
+    from dual_dmp_b200.util.networks import NormalNet, PosNet
+
+    # mode A: every rank fits its own mesh, no data-path collective -> weak scaling
+    n_mesh, s_mesh, ds = build_case(args.n)
+    V, F = len(n_mesh.vs), len(n_mesh.faces)
+    torch.manual_seed(0)
+    posnet, normnet = PosNet(dev).to(dev), NormalNet(dev).to(dev)
+    opt_pos = torch.optim.Adam(posnet.parameters(), lr=0.01)
+    opt_norm = torch.optim.Adam(normnet.parameters(), lr=0.01)
+    k = args.k
+
+    def step(ds_, tgt_vs, tgt_fn, epoch, sync_loss):
+        posnet.train(); normnet.train()
+        opt_pos.zero_grad(); opt_norm.zero_grad()
+        pos = posnet(ds_)
+        l1 = L.pos_rec_loss(pos, tgt_vs)
+        l2 = L.mesh_laplacian_loss(pos, n_mesh)
+        nrm = normnet(ds_)
+        l3 = L.norm_rec_loss(nrm, tgt_fn)
+        l4, _ = L.fn_bnf_loss(pos, nrm, n_mesh, loop=args.bnfloop)
+        if epoch <= 100:
+            l4 = l4 * 0.0
+        l5 = L.pos_norm_loss(pos, nrm, n_mesh)
+        loss = k[0] * l1 + k[1] * l2 + k[2] * l3 + k[3] * l4 + k[4] * l5
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(normnet.parameters(), 0.8)
+        opt_pos.step(); opt_norm.step()
+        return loss.item() if sync_loss else loss
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches0 = lib.query("ddmp_launch_count")
+        e0.record()
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if dist is not None:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), lib.query("ddmp_launch_count") - launches0
+
+    # ---- resident arm: inputs and targets already in HBM -----------------------------------------------------------
+    import copy
+    ds_dev = copy.copy(ds).to(dev)
+    tgt_vs = torch.from_numpy(n_mesh.vs).to(dev)
+    tgt_fn = torch.from_numpy(n_mesh.fn).to(dev)
+    epoch0 = 101   # past the reference's 100-iteration BNF warm-up, so every loss term is live
+
+    # per-launch SpMM timing (CUDA events on the launching stream) inside the timed region
+    spmm_events = []
+    orig_spmm = F_.spmm_gcn
+
+    def spmm_timed(graph, H, *a, **kw):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        out = orig_spmm(graph, H, *a, **kw)
+        e.record()
+        spmm_events.append((s, e, spmm_bytes(graph.n, graph.nnz, H.shape[1]), H.shape[1], graph.n))
+        return out
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    for i in range(args.warmup):
+        step(ds_dev, tgt_vs, tgt_fn, epoch0 + i, False)
+    F_.spmm_gcn = spmm_timed
+    ms, launches = timed(lambda i: step(ds_dev, tgt_vs, tgt_fn, epoch0 + i, False), args.steps, 0)
+    F_.spmm_gcn = orig_spmm
+    sampler.stop_flag = True
+    torch.cuda.synchronize()
+    sp_ms = sum(s.elapsed_time(e) for s, e, _, _, _ in spmm_events)
+    sp_bytes = sum(b for _, _, b, _, _ in spmm_events)
+    n_sp = len(spmm_events)
+    by_width = {}
+    for s, e, b, C, nn in spmm_events:
+        d = by_width.setdefault(f"n={nn},C={C}", [0.0, 0, 0])
+        d[0] += s.elapsed_time(e); d[1] += b; d[2] += 1
+    spmm_events.clear()
+    ms_per_step = ms / args.steps
+    value = world * 1000.0 / ms_per_step
+
+    # ---- end-to-end arm: host buffers, H2D of the step's inputs and D2H of the loss inside the timed region ---------
+    e2e = None
+    if not args.no_e2e:
+        ds_host = copy.copy(ds).pin_memory()
+        vs_host, fn_host = n_mesh.vs, n_mesh.fn          # float64 numpy, uploaded by the loss calls like the reference
+        ms_e, _ = timed(lambda i: step(ds_host, vs_host, fn_host, epoch0 + i, True), args.steps, args.warmup)
+        h2d = ds.z1.numel() * 4 + ds.z2.numel() * 4 + ds.x_pos.numel() * 4 + vs_host.nbytes + fn_host.nbytes
+        e2e = {"value": world * 1000.0 * args.steps / ms_e, "unit": "iters/s", "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": 8}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = sp_bytes / (sp_ms * 1e-3) / 1e9 if sp_ms > 0 else 0.0
+    out = {
+        "metric": METRIC, "value": value, "unit": "iters/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"synthetic icosphere n={args.n}: {F} faces / {V} vertices, Gaussian noise 0.2, "
+                               f"k={args.k}, bnfloop={args.bnfloop}, one independent mesh fit per GPU",
+                   "faces": F, "vertices": V, "l2_policy": "working set (>=10 GB of saved activations) exceeds L2",
+                   "optimizer": "torch.optim.Adam + clip_grad_norm_ (reference main.py:108-110)"},
+        "e2e": e2e, "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "spmm_gcn_kernel (all GCN aggregation launches, fwd+bwd)",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650",
+                     "frac_of_nominal_8000": achieved / 8000.0, "traffic": None,
+                     "launches_per_step": n_sp // max(args.steps, 1), "share_of_step": sp_ms / ms,
+                     "algorithmic_bytes_per_step": sp_bytes // max(args.steps, 1)},
+        "clocks": sampler.summary(),
+    }
+    if args.detail:
+        os.makedirs(os.path.dirname(os.path.abspath(args.detail)), exist_ok=True)
+        json.dump({k_: {"ms_total": v[0], "GBps": v[1] / (v[0] * 1e-3) / 1e9 if v[0] > 0 else None, "launches": v[2]}
+                   for k_, v in by_width.items()}, open(args.detail, "w"), indent=1)
+    if not args.no_cpu_baseline and world == 1:
+        out["cpu_baseline"] = cpu_reference(args, steps=2, warmup=1, target_faces=F)
+    print(json.dumps(out), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_reference(args, steps, warmup, target_faces):
+    """The oracle port of the reference's PyG CPU path (oracle/step_ref.py) on a bounded sample, scaled linearly in
+    the face count to the benchmark mesh.  kind="port": torch_geometric is not installable here."""
+    from oracle import step_ref
+    from oracle.networks_ref import NormalNetRef, PosNetRef
+    n_mesh, s_mesh, _ = build_case(args.cpu_n)
+    ds = step_ref.make_dataset(n_mesh, s_mesh)
+    F = len(n_mesh.faces)
+    best = None
+    for threads in sorted({1, min(8, os.cpu_count() or 1), os.cpu_count() or 1}):
+        torch.set_num_threads(threads)
+        torch.manual_seed(0)
+        posnet, normnet = PosNetRef(), NormalNetRef()
+        opt_pos = torch.optim.Adam(posnet.parameters(), lr=0.01)
+        opt_norm = torch.optim.Adam(normnet.parameters(), lr=0.01)
+        for i in range(warmup):
+            step_ref.train_step(posnet, normnet, opt_pos, opt_norm, ds, n_mesh, tuple(args.k), args.bnfloop, 101 + i)
+        t0 = time.perf_counter()
+        for i in range(steps):
+            step_ref.train_step(posnet, normnet, opt_pos, opt_norm, ds, n_mesh, tuple(args.k), args.bnfloop, 102 + i)
+        dt = (time.perf_counter() - t0) / steps
+        if best is None or dt < best[0]:
+            best = (dt, threads)
+    dt, threads = best
+    return {"value": (1.0 / dt) * (F / float(target_faces)), "unit": "iters/s", "cores": threads, "kind": "port",
+            "sample": f"oracle step on icosphere n={args.cpu_n} ({F} faces): {dt:.3f} s/iter with {threads} threads "
+                      f"(best of 1/8/all), scaled linearly by faces to {target_faces}",
+            "measured_s_per_iter_on_sample": dt, "sample_faces": F}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from dual_dmp_b200 import synth  # noqa: F401  (host-only generator)
+    F_target = 20 * args.n * args.n
+    base = cpu_reference(args, steps=max(1, min(args.steps, 3)), warmup=max(1, min(args.warmup, 1)),
+                         target_faces=F_target)
+    out = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "iters/s",
+           "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": 1000.0 / base["value"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic",
+           "config": {"workload": f"synthetic icosphere n={args.n}: {F_target} faces, k={args.k}, "
+                                  f"bnfloop={args.bnfloop} (CPU: bounded sample, see cpu_baseline.sample)"},
+           "cpu_baseline": base,
+           "e2e": {"value": base["value"], "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -1,0 +1,74 @@
+// Library-level entry points and the error channel of libddmp_b200.
+#include <stdarg.h>
+#include <atomic>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace ddmp {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+long long launch_count() { return g_launches.load(); }
+
+int check_launch(const char* what) {
+    g_launches.fetch_add(1);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: kernel launch failed: %s", what, cudaGetErrorString(e));
+        return DDMP_ERR_CUDA;
+    }
+    return DDMP_OK;
+}
+
+}  // namespace ddmp
+
+extern "C" {
+
+int ddmp_version(void) { return 100; }
+
+int64_t ddmp_launch_count(void) { return (int64_t)ddmp::launch_count(); }
+
+const char* ddmp_last_error(void) { return ddmp::g_err; }
+
+int ddmp_set_device(int device) {
+    int cur = -1;
+    DDMP_CUDA(cudaGetDevice(&cur));
+    if (cur != device) DDMP_CUDA(cudaSetDevice(device));
+    return DDMP_OK;
+}
+
+int ddmp_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+    int dev = 0;
+    DDMP_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp p;
+    DDMP_CUDA(cudaGetDeviceProperties(&p, dev));
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (cc_major) *cc_major = p.major;
+    if (cc_minor) *cc_minor = p.minor;
+    return DDMP_OK;
+}
+
+int ddmp_rows_per_block(int32_t C) {
+    if (C <= 0) return 0;
+    int r = 65536 / C;
+    if (r < 128) r = 128;
+    if (r > 1024) r = 1024;
+    return r;
+}
+
+int64_t ddmp_num_row_blocks(int64_t n, int32_t C) {
+    int r = ddmp_rows_per_block(C);
+    if (r <= 0 || n <= 0) return 0;
+    return (n + r - 1) / r;
+}
+
+}  // extern "C"

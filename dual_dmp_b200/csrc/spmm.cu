@@ -1,0 +1,215 @@
+// GCN aggregation: symmetric-normalised SpMM over CSR, row-segmented, deterministic (no atomics).
+//   Y[i,:] = sum_k w[k] * H[col[k],:] (+ bias), optional BatchNorm partial statistics in the epilogue.
+// Replaces torch_geometric GCNConv.propagate (index_select -> mul -> torch_scatter.scatter_add) called from
+// reference util/networks.py:51-62,112-123, and its backward (A_hat is symmetric, so backward = same kernel).
+//
+// Mapping: a "row group" of G = min(32, C/4) lanes owns one output row at a time and keeps it in NV = C/(4G)
+// float4 accumulators per lane; 128-bit gathers of H rows; the (col, w) stream of a row is fetched with ONE
+// coalesced load per G entries (lane j takes entry j) and broadcast with group-scoped shuffles.  A CTA of 256
+// threads walks `rows_per_block` consecutive rows (consecutive groups take consecutive rows, so neighbour rows
+// gathered by one CTA overlap in L1).  Roofline: HBM; algorithmic bytes 4*[(n+1) + 2*nnz + 2*n*C].
+#include "common.cuh"
+
+namespace ddmp {
+
+template <int C, bool STATS, bool BIAS>
+__global__ void __launch_bounds__(256)
+spmm_gcn_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const float* __restrict__ w,
+                const float* __restrict__ H, const float* __restrict__ bias, float* __restrict__ Y,
+                float* __restrict__ partials, int64_t n, int rows_per_block) {
+    constexpr int G = (C / 4 < 32) ? (C / 4) : 32;
+    constexpr int NV = C / (4 * G);
+    constexpr int GROUPS = 256 / G;
+    constexpr int U = (NV >= 4) ? 2 : 4;
+
+    const int lane = threadIdx.x & 31;
+    const int lg = lane % G;
+    const int gid = threadIdx.x / G;
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((lane / G) * G));
+
+    const int64_t row0 = (int64_t)blockIdx.x * rows_per_block;
+    const int64_t row_end = (row0 + rows_per_block < n) ? (row0 + rows_per_block) : n;
+
+    float4 bsum[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        bsum[v] = BIAS ? ldg4(bias + (v * G + lg) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float4 s[NV], q[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        s[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        q[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+
+    for (int64_t r = row0 + gid; r < row_end; r += GROUPS) {
+        const int start = __ldg(rowptr + r);
+        const int end = __ldg(rowptr + r + 1);
+        float4 acc[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+        for (int k0 = start; k0 < end; k0 += G) {
+            const int kk = k0 + lg;
+            const int myc = (kk < end) ? __ldg(col + kk) : 0;
+            const float myw = (kk < end) ? __ldg(w + kk) : 0.f;
+            const int cnt = (end - k0 < G) ? (end - k0) : G;
+            int j = 0;
+            for (; j + U <= cnt; j += U) {
+                int cj[U];
+                float wj[U];
+                float4 x[U][NV];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    cj[u] = __shfl_sync(gmask, myc, j + u, G);
+                    wj[u] = __shfl_sync(gmask, myw, j + u, G);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const float* hp = H + (int64_t)cj[u] * C;
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) x[u][v] = ldg4(hp + (v * G + lg) * 4);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) {
+                        acc[v].x = fmaf(wj[u], x[u][v].x, acc[v].x);
+                        acc[v].y = fmaf(wj[u], x[u][v].y, acc[v].y);
+                        acc[v].z = fmaf(wj[u], x[u][v].z, acc[v].z);
+                        acc[v].w = fmaf(wj[u], x[u][v].w, acc[v].w);
+                    }
+                }
+            }
+            for (; j < cnt; ++j) {
+                const int c1 = __shfl_sync(gmask, myc, j, G);
+                const float w1 = __shfl_sync(gmask, myw, j, G);
+                const float* hp = H + (int64_t)c1 * C;
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    const float4 x = ldg4(hp + (v * G + lg) * 4);
+                    acc[v].x = fmaf(w1, x.x, acc[v].x);
+                    acc[v].y = fmaf(w1, x.y, acc[v].y);
+                    acc[v].z = fmaf(w1, x.z, acc[v].z);
+                    acc[v].w = fmaf(w1, x.w, acc[v].w);
+                }
+            }
+        }
+        float* yp = Y + r * C;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            float4 o = acc[v];
+            if (BIAS) {
+                o.x += bsum[v].x; o.y += bsum[v].y; o.z += bsum[v].z; o.w += bsum[v].w;
+            }
+            st4(yp + (v * G + lg) * 4, o);
+            if (STATS) {
+                s[v].x += o.x; s[v].y += o.y; s[v].z += o.z; s[v].w += o.w;
+                q[v].x = fmaf(o.x, o.x, q[v].x); q[v].y = fmaf(o.y, o.y, q[v].y);
+                q[v].z = fmaf(o.z, o.z, q[v].z); q[v].w = fmaf(o.w, o.w, q[v].w);
+            }
+        }
+    }
+
+    if (STATS) {
+        // combine the GROUPS row groups of this CTA channel-wise in a fixed order
+        __shared__ float red[GROUPS * C];
+        float* outp = partials + (int64_t)blockIdx.x * 2 * C;
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                st4(red + gid * C + (v * G + lg) * 4, pass == 0 ? s[v] : q[v]);
+            }
+            __syncthreads();
+            for (int c = threadIdx.x; c < C; c += 256) {
+                float t = 0.f;
+#pragma unroll 8
+                for (int g = 0; g < GROUPS; ++g) t += red[g * C + c];
+                outp[pass * C + c] = t;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// Any width: one warp per row, lanes stride over channels (operator-level GCNConv with unusual widths).
+__global__ void __launch_bounds__(256)
+spmm_gcn_generic_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const float* __restrict__ w,
+                        const float* __restrict__ H, const float* __restrict__ bias, float* __restrict__ Y,
+                        int64_t n, int C) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= n) return;
+    const int start = rowptr[r], end = rowptr[r + 1];
+    for (int c = lane; c < C; c += 32) {
+        float acc = 0.f;
+        for (int k = start; k < end; ++k) acc = fmaf(__ldg(w + k), __ldg(H + (int64_t)__ldg(col + k) * C + c), acc);
+        Y[r * C + c] = acc + (bias ? bias[c] : 0.f);
+    }
+}
+
+__global__ void gcn_edge_weights_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
+                                        float* __restrict__ w, int64_t n) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const int start = rowptr[r], end = rowptr[r + 1];
+    // deg^-1/2 as an IEEE 1/sqrt, like torch.pow(deg, -0.5) on the reference path
+    const float di = 1.0f / sqrtf((float)(end - start));
+    for (int k = start; k < end; ++k) {
+        const int j = col[k];
+        const float dj = 1.0f / sqrtf((float)(rowptr[j + 1] - rowptr[j]));
+        w[k] = di * dj;
+    }
+}
+
+template <int C>
+static int launch_spmm(const int* rowptr, const int* col, const float* w, const float* H, const float* bias,
+                       float* Y, float* partials, int64_t n, cudaStream_t st) {
+    const int rpb = ddmp_rows_per_block(C);
+    const unsigned grid = (unsigned)ceil_div(n, rpb);
+    if (partials) {
+        if (bias) spmm_gcn_kernel<C, true, true><<<grid, 256, 0, st>>>(rowptr, col, w, H, bias, Y, partials, n, rpb);
+        else spmm_gcn_kernel<C, true, false><<<grid, 256, 0, st>>>(rowptr, col, w, H, bias, Y, partials, n, rpb);
+    } else {
+        if (bias) spmm_gcn_kernel<C, false, true><<<grid, 256, 0, st>>>(rowptr, col, w, H, bias, Y, partials, n, rpb);
+        else spmm_gcn_kernel<C, false, false><<<grid, 256, 0, st>>>(rowptr, col, w, H, bias, Y, partials, n, rpb);
+    }
+    return check_launch("spmm_gcn");
+}
+
+}  // namespace ddmp
+
+extern "C" {
+
+int ddmp_gcn_edge_weights(const int32_t* rowptr, const int32_t* col, float* w, int64_t n, void* stream) {
+    DDMP_REQUIRE(rowptr && col && w && n >= 0, "gcn_edge_weights: null pointer or negative n");
+    if (n == 0) return DDMP_OK;
+    ddmp::gcn_edge_weights_kernel<<<(unsigned)ddmp::ceil_div(n, 256), 256, 0, ddmp::as_stream(stream)>>>(rowptr, col, w, n);
+    return ddmp::check_launch("gcn_edge_weights");
+}
+
+int ddmp_spmm_gcn(const int32_t* rowptr, const int32_t* col, const float* w, const float* H, const float* bias,
+                  float* Y, float* stats_partials, int64_t n, int32_t C, void* stream) {
+    using namespace ddmp;
+    DDMP_REQUIRE(rowptr && col && w && H && Y, "spmm_gcn: null pointer");
+    DDMP_REQUIRE(n >= 0 && C > 0, "spmm_gcn: bad shape n=%lld C=%d", (long long)n, C);
+    if (n == 0) return DDMP_OK;
+    cudaStream_t st = as_stream(stream);
+    switch (C) {
+        case 32: return launch_spmm<32>(rowptr, col, w, H, bias, Y, stats_partials, n, st);
+        case 64: return launch_spmm<64>(rowptr, col, w, H, bias, Y, stats_partials, n, st);
+        case 128: return launch_spmm<128>(rowptr, col, w, H, bias, Y, stats_partials, n, st);
+        case 256: return launch_spmm<256>(rowptr, col, w, H, bias, Y, stats_partials, n, st);
+        case 512: return launch_spmm<512>(rowptr, col, w, H, bias, Y, stats_partials, n, st);
+        default: break;
+    }
+    if (stats_partials) {
+        set_error("spmm_gcn: BatchNorm statistics epilogue supports C in {32,64,128,256,512}, got %d", C);
+        return DDMP_ERR_UNSUPPORTED;
+    }
+    spmm_gcn_generic_kernel<<<(unsigned)ceil_div(n, 8), 256, 0, st>>>(rowptr, col, w, H, bias, Y, n, C);
+    return check_launch("spmm_gcn_generic");
+}
+
+}  // extern "C"

@@ -1,0 +1,201 @@
+/* libddmp_b200 — C ABI of the B200-native Dual-DMP training hot path.
+ *
+ * The reference (astaka-pe/Dual-DMP) is pure Python and has no FFI; every entry point below replaces a LIBRARY
+ * call site of its hot path (torch_geometric.GCNConv / torch_scatter / torch.nn / torch ops).  The reference
+ * location each one replaces is cited as  [ref: file:line].  The Python binding is dual_dmp_b200/_lib.py (ctypes);
+ * INTEGRATION.md shows the reference-side change.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch allocates everything); the library never
+ *     allocates, frees or keeps device memory, and holds no mutable global state;
+ *   - tensors are contiguous row-major float32 unless stated; indices are int32; `n` rows are int64;
+ *   - `stream` is a cudaStream_t (torch.cuda.current_stream().cuda_stream); all work is enqueued on it and no
+ *     call synchronises the host;
+ *   - return value 0 = ok, <0 = error (DDMP_ERR_*); ddmp_last_error() returns a thread-local message;
+ *   - entry points are re-entrant (autograd runs backward on another thread); call ddmp_set_device() on the
+ *     calling thread first when more than one GPU is visible;
+ *   - results are deterministic: no floating-point atomics anywhere; reductions combine partials in a fixed
+ *     order.
+ */
+#ifndef DDMP_B200_H
+#define DDMP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DDMP_OK 0
+#define DDMP_ERR_INVALID (-1)
+#define DDMP_ERR_CUDA (-2)
+#define DDMP_ERR_UNSUPPORTED (-3)
+
+#define DDMP_GEMM_AUTO 0
+#define DDMP_GEMM_FFMA 1  /* fp32 FFMA kernel                                  */
+#define DDMP_GEMM_TC 2    /* tcgen05 tensor cores, 3xTF32 split, fp32 accumulate */
+
+#define DDMP_HEAD_POS 0
+#define DDMP_HEAD_NORM 1
+
+/* ---- library ------------------------------------------------------------------------------------------- */
+int ddmp_version(void);
+const char* ddmp_last_error(void);
+int ddmp_set_device(int device);
+/* number of CUDA kernels this library has launched in this process (bench.py reports the per-step count). */
+int64_t ddmp_launch_count(void);
+/* sm count / compute capability of the current device; fails (DDMP_ERR_CUDA) when no CUDA device is usable. */
+int ddmp_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* rows covered by one partial-statistics block for channel width C (all *_partials arguments below are
+ * [ddmp_num_row_blocks(n, C)][sets][C] float32). */
+int ddmp_rows_per_block(int32_t C);
+int64_t ddmp_num_row_blocks(int64_t n, int32_t C);
+
+/* ---- graph --------------------------------------------------------------------------------------------- */
+/* GCN symmetric normalisation, hoisted out of the step.  CSR rows are TARGET nodes and already contain exactly
+ * one self loop per node:  w[k] = deg(row)^-1/2 * deg(col[k])^-1/2, deg(i) = rowptr[i+1]-rowptr[i].
+ * [ref: torch_geometric gcn_norm, recomputed 24x per step at util/networks.py:51-62,112-123] */
+int ddmp_gcn_edge_weights(const int32_t* rowptr, const int32_t* col, float* w, int64_t n, void* stream);
+
+/* ---- GCN aggregation ------------------------------------------------------------------------------------ */
+/* Y[i,:] = sum_k w[k] * H[col[k],:] (+ bias).  Optional epilogue statistics: stats_partials[b][0][c] = sum of
+ * Y[:,c] over row block b, [b][1][c] = sum of Y^2 (BatchNorm partials).  The same call is the backward pass
+ * (A_hat is symmetric): dH = spmm(dY) with bias = stats = NULL.  C must be a multiple of 4.
+ * [ref: GCNConv.propagate + bias at util/networks.py:51-62,112-123; torch_scatter.scatter_add] */
+int ddmp_spmm_gcn(const int32_t* rowptr, const int32_t* col, const float* w, const float* H, const float* bias,
+                  float* Y, float* stats_partials, int64_t n, int32_t C, void* stream);
+
+/* ---- BatchNorm1d (training mode) + LeakyReLU ------------------------------------------------------------ */
+/* partials [nblk][2][C] -> batch mean / biased var; rstd = 1/sqrt(var+eps); scale = gamma*rstd;
+ * shift = beta - mean*scale; running stats updated in place when non-NULL (momentum, unbiased var).
+ * The normalise + LeakyReLU itself is applied lazily by the consumer (GEMM / head prologue).
+ * [ref: nn.BatchNorm1d at util/networks.py:31-42,51-62] */
+int ddmp_bn_stats_finalize(const float* partials, int64_t nblk, int64_t n, int32_t C, const float* gamma,
+                           const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                           float* mean, float* rstd, float* scale, float* shift, void* stream);
+/* Backward of LeakyReLU(BN(Y)) given gX = dL/d(activated output):  gZ = gX * lrelu'(scale*Y+shift),
+ * xhat = (Y-mean)*rstd;  partials[b][0][c] = sum gZ, [b][1][c] = sum gZ*xhat. */
+int ddmp_bn_bwd_reduce(const float* gX, const float* Y, const float* mean, const float* rstd, const float* scale,
+                       const float* shift, float slope, float* partials, int64_t n, int32_t C, void* stream);
+/* dgamma = sum gZ*xhat, dbeta = sum gZ, c1 = dbeta/n, c2 = dgamma/n. */
+int ddmp_bn_bwd_finalize(const float* partials, int64_t nblk, int64_t n, int32_t C, float* dgamma, float* dbeta,
+                         float* c1, float* c2, void* stream);
+/* dY = scale * (gZ - c1 - xhat*c2);  optional colsum_partials[b][0][c] = sum of dY (the conv bias gradient). */
+int ddmp_bn_bwd_apply(const float* gX, const float* Y, const float* mean, const float* rstd, const float* scale,
+                      const float* shift, float slope, const float* c1, const float* c2, float* dY,
+                      float* colsum_partials, int64_t n, int32_t C, void* stream);
+/* out[s][c] = sum_b partials[b][s][c]  (fixed order, float64 accumulate). */
+int ddmp_colsum_finalize(const float* partials, int64_t nblk, int32_t sets, int32_t C, float* out, void* stream);
+/* partials[b][0][c] = sum over row block b of X[:,c]  (bias gradients of the heads). */
+int ddmp_colsum_partials(const float* X, float* partials, int64_t n, int32_t C, void* stream);
+
+/* ---- dense feature transform ------------------------------------------------------------------------------ */
+/* H[n,Cout] = act(X)[n,Cin] * W[Cout,Cin]^T.   act(x)[i,k] = lrelu(scale[k]*X[r,k]+shift[k]) when scale != NULL
+ * (the previous layer's BatchNorm+LeakyReLU applied on load), r = row_map[i] when row_map != NULL (first-layer
+ * gather from the caller's numbering into the space-filling-curve order).
+ * [ref: GCNConv.lin at util/networks.py:51-62 — cuBLAS SGEMM] */
+int ddmp_gemm_xw(const float* X, const int32_t* row_map, const float* scale, const float* shift, float slope,
+                 const float* W, float* H, int64_t n, int32_t Cin, int32_t Cout, int backend, void* stream);
+/* gX[n,Cin] = dH[n,Cout] * W[Cout,Cin]. */
+int ddmp_gemm_dx(const float* dH, const float* W, float* gX, int64_t n, int32_t Cin, int32_t Cout, int backend,
+                 void* stream);
+/* dW[Cout,Cin] = dH[n,Cout]^T * act(X)[n,Cin]; deterministic split-K over rows through `workspace`. */
+int64_t ddmp_gemm_dw_workspace_bytes(int64_t n, int32_t Cin, int32_t Cout);
+int ddmp_gemm_dw(const float* dH, const float* X, const int32_t* row_map, const float* scale, const float* shift,
+                 float slope, float* dW, void* workspace, int64_t workspace_bytes, int64_t n, int32_t Cin,
+                 int32_t Cout, int backend, void* stream);
+
+/* ---- network heads (32 -> 16 -> 3) ------------------------------------------------------------------------ */
+/* x = lrelu(scale*Y12+shift); h = lrelu(W1 x + b1); o = W2 h + b2;
+ * POS : out[p] = x_pos[p] + o                      [ref: util/networks.py:64-67]
+ * NORM: t = tanh(o); out[p] = t / (||t|| + 1e-12)   [ref: util/networks.py:125-129]
+ * p = perm[i] (row i of the reordered graph is node perm[i] of the caller) or i when perm == NULL.
+ * h_save [n,16] and t_save [n,4] = (t, ||t||) (NORM only) are kept for the backward pass. */
+int ddmp_head_fwd(int kind, const float* Y12, const float* scale, const float* shift, float slope, const float* W1,
+                  const float* b1, const float* W2, const float* b2, const int32_t* perm, const float* x_pos,
+                  float* out, float* h_save, float* t_save, int64_t n, void* stream);
+/* g_out [n,3] in the caller's numbering ->  go [n,4] = (dL/do, 0), gh [n,16] = dL/d(pre-activation of linear1),
+ * gX12 [n,32] = dL/dx (input of linear1, i.e. the activated trunk output); all three in reordered rows. */
+int ddmp_head_bwd(int kind, const float* g_out, const int32_t* perm, const float* W1, const float* W2,
+                  const float* h_save, const float* t_save, float slope, float* go, float* gh, float* gX12,
+                  int64_t n, void* stream);
+
+/* ---- losses ---------------------------------------------------------------------------------------------- */
+/* Scalar results are written to device memory; `scratch` is a caller-provided zero-initialised buffer of at
+ * least ddmp_loss_scratch_bytes() bytes that the kernels leave zeroed again (ticket counter + partials). */
+int64_t ddmp_loss_scratch_bytes(void);
+/* sqrt(mean_v ||pos-target||^2 + 1e-6), float64 like the reference's promotion. [ref: util/loss.py:16-35] */
+int ddmp_loss_pos_rec_fwd(const float* pos, const double* target, double* loss, void* scratch, int64_t V,
+                          void* stream);
+int ddmp_loss_pos_rec_bwd(const float* pos, const double* target, const double* loss, const double* gout,
+                          float* gpos, int64_t V, void* stream);
+/* uniform Laplacian: d_i = pos_i - mean_{j in N(i)} pos_j; sqrt(mean ||d||^2 + 1e-12).  (rowptr, col) is the
+ * unweighted vertex adjacency WITHOUT self loops.  d [V,3] is kept for backward. [ref: util/loss.py:37-53] */
+int ddmp_loss_lap_fwd(const float* pos, const int32_t* rowptr, const int32_t* col, float* d, float* loss,
+                      void* scratch, int64_t V, void* stream);
+int ddmp_loss_lap_bwd(const float* d, const int32_t* rowptr, const int32_t* col, const float* loss,
+                      const float* gout, float* gpos, int64_t V, void* stream);
+/* mean_f ||norm - target||_1, float64. [ref: util/loss.py:55-84 "l1mae"] */
+int ddmp_loss_norm_rec_fwd(const float* nrm, const double* target, double* loss, void* scratch, int64_t F,
+                           void* stream);
+int ddmp_loss_norm_rec_bwd(const float* nrm, const double* target, const double* gout, float* gnrm, int64_t F,
+                           void* stream);
+/* sum_f sum_k |(p_fk - c_f).n_f| / V.  Backward: gnrm per face; gpos through the corner CSR (corner_ptr [V+1],
+ * corner_slot [3F] = 3*f+k of every corner incident to a vertex), deterministic gather instead of scatter-add;
+ * face_tmp is [F,9] scratch. [ref: util/loss.py:140-160 "mae"] */
+int ddmp_loss_pos_norm_fwd(const float* pos, const float* nrm, const int32_t* faces, float* loss, void* scratch,
+                           int64_t V, int64_t F, void* stream);
+int ddmp_loss_pos_norm_bwd(const float* pos, const float* nrm, const int32_t* faces, const int32_t* corner_ptr,
+                           const int32_t* corner_slot, const float* gout, float* face_tmp, float* gpos,
+                           float* gnrm, int64_t V, int64_t F, void* stream);
+/* Bilateral normal filtering loss [ref: util/loss.py:86-138 "l1mae"].
+ * setup: from (detached) pos: centroid / area / centroid distance per slot, global sigma_c, then
+ *        wca[f,s] = exp(-dist/(2 sigma_c^2)) * area[f2f[f,s]] * (f2f[f,s] != -1); a -1 slot reads face F-1
+ *        (Python negative indexing) and still counts in sigma_c, exactly like the reference (:99-103).
+ * iter_fwd: n_out = normalise(sum_s wca*exp(-||n_j-n_i||^2/(2*0.3^2)) n_j)
+ * loss: mean_f ||n_L - n_0||_1 ; iter_bwd: gradient through one iteration via the reverse-slot map rslot[f,s]
+ *        (position of f in the row of its s-th neighbour), no atomics; msg is [F,9] scratch. */
+int ddmp_bnf_setup(const float* pos, const int32_t* faces, const int32_t* f2f, float* fc, float* fa, float* wca,
+                   float* sigma_c, void* scratch, int64_t F, void* stream);
+int ddmp_bnf_iter_fwd(const float* n_in, const int32_t* f2f, const float* wca, float* n_out, int64_t F,
+                      void* stream);
+int ddmp_bnf_loss_fwd(const float* n_last, const float* n_first, float* loss, void* scratch, int64_t F,
+                      void* stream);
+/* g_last = gout*sign(n_last-n_first)/F ; g_first_direct = -g_last */
+int ddmp_bnf_loss_bwd(const float* n_last, const float* n_first, const float* gout, float* g_last, int64_t F,
+                      void* stream);
+/* g_in = d(loss)/d(n_in) through one iteration, minus g_sub when g_sub != NULL (the direct -sign/F term of the
+ * loss with respect to the unfiltered normals, folded into the first iteration's backward). */
+int ddmp_bnf_iter_bwd(const float* n_in, const float* g_out, const int32_t* f2f, const int32_t* rslot,
+                      const float* wca, const float* g_sub, float* msg, float* g_in, int64_t F, void* stream);
+
+/* ---- geometry / evaluation ---------------------------------------------------------------------------------- */
+/* fn = cross(p1-p0, p2-p0) / ||.||  (no epsilon) [ref: util/models.py:5-10]; backward through the corner CSR. */
+int ddmp_face_normals_fwd(const float* pos, const int32_t* faces, float* fn, int64_t F, void* stream);
+int ddmp_face_normals_bwd(const float* pos, const int32_t* faces, const int32_t* corner_ptr,
+                          const int32_t* corner_slot, const float* gfn, float* face_tmp, float* gpos, int64_t V,
+                          int64_t F, void* stream);
+/* mean angular distance in degrees between two sets of unit normals, float64 [ref: util/loss.py:261-272]. */
+int ddmp_mad(const float* n1, const float* n2, double* out, void* scratch, int64_t F, void* stream);
+/* vertex normals: normalise(sum of incident face normals) through the corner CSR [ref: util/models.py:12-29]. */
+int ddmp_vertex_normals(const float* fn, const int32_t* corner_ptr, const int32_t* corner_slot, float* vn,
+                        int64_t V, void* stream);
+/* One Jacobi sweep of the normal-guided vertex update [ref: util/models.py:31-44]: fc is the centroid array of
+ * the sweep's input positions. */
+int ddmp_vertex_update_sweep(const float* pos_in, const float* fc, const float* nrm, const int32_t* corner_ptr,
+                             const int32_t* corner_slot, float* pos_out, int64_t V, void* stream);
+int ddmp_face_centroids(const float* pos, const int32_t* faces, float* fc, int64_t F, void* stream);
+
+/* ---- step glue ----------------------------------------------------------------------------------------------- */
+/* Global L2 norm of a flat gradient buffer (float64 accumulate) -> norm_out[0]; then the Adam update with the
+ * clip coefficient min(1, max_norm/(norm+1e-6)) folded in (clip_norm == NULL: no clipping).
+ * [ref: main.py:108-110 clip_grad_norm_ + torch.optim.Adam(lr, betas=(0.9,0.999), eps=1e-8)] */
+int ddmp_grad_norm(const float* grad, float* norm_out, void* scratch, int64_t count, void* stream);
+int ddmp_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, const float* clip_norm,
+                   float max_norm, float lr, float beta1, float beta2, float eps, int64_t step, int64_t count,
+                   void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DDMP_B200_H */

@@ -1,0 +1,259 @@
+"""Kernel-level parity (through the C ABI) against the CPU oracle / plain torch fp32-fp64 evaluations."""
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import rel_err, report, small_case
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def graphs():
+    from dual_dmp_b200.graph import GcnGraph
+    from oracle.step_ref import make_dataset
+    out = {}
+    for kind, n in (("ico", 10), ("open", 9)):
+        n_mesh, s_mesh, _ = small_case(kind, n)
+        ds = make_dataset(n_mesh, s_mesh)
+        V, F = len(n_mesh.vs), len(n_mesh.faces)
+        out[kind] = dict(
+            mesh=n_mesh, ds=ds,
+            vg=GcnGraph(ds.edge_index, V, DEV, coords=ds.x_pos, reorder=True),
+            vg_id=GcnGraph(ds.edge_index, V, DEV, reorder=False),
+            fg=GcnGraph(ds.face_index, F, DEV, coords=ds.z2.detach()[:, :3], reorder=True),
+            fg_id=GcnGraph(ds.face_index, F, DEV, reorder=False))
+    return out
+
+
+def _ref_aggregate(edge_index, n, H):
+    from oracle.gcn_ref import gcn_norm_ref
+    idx, w = gcn_norm_ref(edge_index, n, torch.float64)
+    out = torch.zeros(n, H.shape[1], dtype=torch.float64)
+    return out.index_add_(0, idx[1], w.view(-1, 1) * H.double().index_select(0, idx[0]))
+
+
+@pytest.mark.parametrize("kind", ["ico", "open"])
+def test_graph_is_bit_exact_and_weights_match(graphs, kind):
+    from oracle.gcn_ref import gcn_norm_ref
+    g = graphs[kind]
+    for graph, ei in ((g["vg"], g["ds"].edge_index), (g["fg"], g["ds"].face_index), (g["vg_id"], g["ds"].edge_index)):
+        idx, w = gcn_norm_ref(ei, graph.n)
+        ref = idx.numpy()
+        ref = ref[:, np.lexsort((ref[1], ref[0]))]
+        assert np.array_equal(graph.to_edge_list(), ref)          # integer part: bit-exact
+        assert graph.symmetric
+        # weights: compare per (src, dst) pair
+        rowptr = graph.rowptr.cpu().numpy().astype(np.int64)
+        dst = np.repeat(np.arange(graph.n), np.diff(rowptr))
+        p = graph.perm_host
+        key = p[graph.col.cpu().numpy()] * graph.n + p[dst]
+        wmap = dict(zip(key.tolist(), graph.w.cpu().numpy().tolist()))
+        kref = (idx[0] * graph.n + idx[1]).numpy()
+        got = np.array([wmap[k] for k in kref.tolist()], dtype=np.float32)
+        assert np.abs(got - w.numpy()).max() <= 2.4e-7 * np.abs(w.numpy()).max()
+        perm = np.sort(p)
+        assert np.array_equal(perm, np.arange(graph.n))
+
+
+@pytest.mark.parametrize("C", [32, 64, 128, 256, 512, 12, 3])
+@pytest.mark.parametrize("which", ["vg_id", "fg_id"])
+def test_spmm_matches_oracle(graphs, C, which):
+    from dual_dmp_b200 import functional as F_
+    g = graphs["open"]
+    graph = g[which]
+    ei = g["ds"].edge_index if which.startswith("v") else g["ds"].face_index
+    torch.manual_seed(C)
+    H = torch.randn(graph.n, C)
+    bias = torch.randn(C)
+    ref = _ref_aggregate(ei, graph.n, H) + bias.double()
+    Hd, bd = H.to(DEV), bias.to(DEV)
+    if C in (32, 64, 128, 256, 512):
+        Y, partials = F_.spmm_gcn(graph, Hd, bias=bd, stats=True)
+        s = partials.double().sum(dim=0).cpu()
+        assert rel_err(s[0], ref.sum(dim=0)) < 1e-5
+        assert rel_err(s[1], (ref * ref).sum(dim=0)) < 1e-5
+        Y2, partials2 = F_.spmm_gcn(graph, Hd, bias=bd, stats=True)
+        assert torch.equal(Y, Y2) and torch.equal(partials, partials2)          # deterministic
+        Y3 = F_.spmm_gcn(graph, Hd)
+        assert rel_err(Y3, ref - bias.double()) < 2e-6
+    else:
+        Y = F_.spmm_gcn(graph, Hd, bias=bd)
+    e = rel_err(Y, ref)
+    report(f"spmm C={C} {which}", e)
+    assert e < 2e-6
+
+
+def test_spmm_reordered_graph_equals_permuted_reference(graphs):
+    from dual_dmp_b200 import functional as F_
+    g = graphs["ico"]
+    graph, ei = g["fg"], g["ds"].face_index
+    H = torch.randn(graph.n, 64)
+    ref = _ref_aggregate(ei, graph.n, H)
+    p = torch.from_numpy(graph.perm_host)
+    Y = F_.spmm_gcn(graph, H[p].contiguous().to(DEV))          # rows in Morton order
+    assert rel_err(Y.cpu(), ref[p]) < 2e-6
+
+
+SHAPES = [(7, 32), (16, 32), (32, 64), (64, 128), (128, 256), (256, 512), (512, 256), (64, 32), (32, 16), (20, 12)]
+
+
+@pytest.mark.parametrize("cin,cout", SHAPES)
+@pytest.mark.parametrize("n", [1000, 4099])
+def test_gemm_ffma(cin, cout, n):
+    from dual_dmp_b200 import functional as F_
+    torch.manual_seed(cin * 1000 + cout)
+    X = torch.randn(n + 5, cin)
+    W = torch.randn(cout, cin) / cin ** 0.5
+    scale, shift = torch.rand(cin) + 0.5, torch.randn(cin)
+    rmap = torch.randperm(n + 5)[:n].to(torch.int32)
+    dH = torch.randn(n, cout)
+    Xd, Wd, dHd = X.to(DEV), W.to(DEV), dH.to(DEV)
+    sc, sh, rm = scale.to(DEV), shift.to(DEV), rmap.to(DEV)
+    act = torch.nn.functional.leaky_relu(X.double() * scale.double() + shift.double(), 0.01)
+    # xw: plain, with BN+LeakyReLU prologue, with row gather
+    e1 = rel_err(F_.gemm_xw(Xd[:n].contiguous(), Wd, backend=1), X[:n].double() @ W.double().t())
+    e2 = rel_err(F_.gemm_xw(Xd[:n].contiguous(), Wd, scale=sc, shift=sh, backend=1), act[:n] @ W.double().t())
+    e3 = rel_err(F_.gemm_xw(Xd, Wd, row_map=rm, n=n, backend=1), X[rmap.long()].double() @ W.double().t())
+    # dx
+    e4 = rel_err(F_.gemm_dx(dHd, Wd, backend=1), dH.double() @ W.double())
+    # dw: plain, prologue, gather
+    e5 = rel_err(F_.gemm_dw(dHd, Xd[:n].contiguous(), cin, backend=1), dH.double().t() @ X[:n].double())
+    e6 = rel_err(F_.gemm_dw(dHd, Xd[:n].contiguous(), cin, scale=sc, shift=sh, backend=1), dH.double().t() @ act[:n])
+    e7 = rel_err(F_.gemm_dw(dHd, Xd, cin, row_map=rm, backend=1), dH.double().t() @ X[rmap.long()].double())
+    report(f"gemm_ffma cin={cin} cout={cout} n={n}", (e1, e2, e3, e4, e5, e6, e7))
+    assert max(e1, e2, e3, e4) < 5e-6, (e1, e2, e3, e4)
+    assert max(e5, e6, e7) < 2e-5, (e5, e6, e7)
+    a = F_.gemm_dw(dHd, Xd[:n].contiguous(), cin, backend=1)
+    b = F_.gemm_dw(dHd, Xd[:n].contiguous(), cin, backend=1)
+    assert torch.equal(a, b)                                                    # split-K is deterministic
+
+
+@pytest.mark.parametrize("C", [32, 64, 256, 512])
+@pytest.mark.parametrize("n", [777, 5000])
+def test_batchnorm_lrelu_forward_backward(C, n):
+    """statistics finalize + lazy apply + backward against torch BatchNorm1d(train) -> LeakyReLU in float64"""
+    from dual_dmp_b200 import functional as F_
+    from dual_dmp_b200.graph import GcnGraph
+    torch.manual_seed(n + C)
+    # statistics come from the SpMM epilogue: aggregate over a graph of isolated nodes (A_hat = I)
+    graph = GcnGraph(torch.zeros(2, 0, dtype=torch.long), n, DEV, reorder=False)
+    Y0 = (torch.randn(n, C) * (torch.rand(C) * 3 + 0.1) + torch.randn(C) * 2)
+    gamma, beta = torch.rand(C) + 0.5, torch.randn(C)
+    rm0, rv0 = torch.randn(C), torch.rand(C) + 0.5
+    bn = torch.nn.BatchNorm1d(C).double()
+    with torch.no_grad():
+        bn.weight.copy_(gamma); bn.bias.copy_(beta); bn.running_mean.copy_(rm0); bn.running_var.copy_(rv0)
+    yr = Y0.double().requires_grad_(True)
+    xr = torch.nn.functional.leaky_relu(bn(yr), 0.01)
+    gX = torch.randn(n, C)
+    xr.backward(gX.double())
+
+    Yd = Y0.to(DEV)
+    Y, partials = F_.spmm_gcn(graph, Yd, stats=True)
+    assert torch.equal(Y, Yd)
+    rm, rv = rm0.to(DEV), rv0.to(DEV)
+    st = F_.bn_stats_finalize(partials, n, gamma.to(DEV), beta.to(DEV), rm, rv)
+    assert rel_err(rm, bn.running_mean) < 1e-5 and rel_err(rv, bn.running_var) < 1e-5
+    x = torch.nn.functional.leaky_relu(Y * st[2] + st[3], 0.01)
+    e_f = rel_err(x, xr)
+    dY, dgamma, dbeta, dbias = F_.bn_lrelu_backward(gX.to(DEV), Y, st)
+    e_b = (rel_err(dY, yr.grad), rel_err(dgamma, bn.weight.grad), rel_err(dbeta, bn.bias.grad))
+    report(f"bn C={C} n={n}", (e_f,) + e_b)
+    assert e_f < 1e-5 and max(e_b) < 2e-5, (e_f, e_b)
+    assert dbias.abs().max() < 1e-3 * dY.abs().sum(dim=0).max()          # true gradient of a pre-BN bias is 0
+    assert rel_err(F_.colsum(Y), Y0.double().sum(dim=0)) < 1e-5
+
+
+@pytest.mark.parametrize("kind", [0, 1])
+def test_heads(kind):
+    from dual_dmp_b200._lib import lib, ptr, stream_ptr
+    torch.manual_seed(kind)
+    n = 3001
+    Y12 = torch.randn(n, 32)
+    scale, shift = torch.rand(32) + 0.5, torch.randn(32) * 0.3
+    lin1, lin2 = torch.nn.Linear(32, 16).double(), torch.nn.Linear(16, 3).double()
+    x_pos = torch.randn(n, 3)
+    perm = torch.randperm(n)
+    g_out = torch.randn(n, 3)
+    # float64 torch reference in the caller's numbering: row i of the reordered tensors is node perm[i]
+    yr = Y12.double().requires_grad_(True)
+    x = torch.nn.functional.leaky_relu(yr * scale.double() + shift.double(), 0.01)
+    x.retain_grad()
+    h = torch.nn.functional.leaky_relu(lin1(x), 0.01)
+    o = lin2(h)
+    if kind == 0:
+        res = x_pos.double()[perm] + o
+    else:
+        t = torch.tanh(o)
+        res = t * torch.reciprocal(torch.norm(t, dim=1, keepdim=True).expand(-1, 3) + 1e-12)
+    res.backward(g_out.double()[perm])
+
+    d = lambda t: t.float().contiguous().to(DEV)
+    out = torch.empty(n, 3, device=DEV)
+    h_save = torch.empty(n, 16, device=DEV)
+    t_save = torch.empty(n, 4, device=DEV)
+    W1, b1, W2, b2 = d(lin1.weight.detach()), d(lin1.bias.detach()), d(lin2.weight.detach()), d(lin2.bias.detach())
+    permd = perm.to(torch.int32).to(DEV)
+    st = stream_ptr(torch.device(DEV))
+    Yd = d(Y12)
+    lib.call("ddmp_head_fwd", kind, ptr(Yd), ptr(d(scale)), ptr(d(shift)), 0.01, ptr(W1), ptr(b1), ptr(W2), ptr(b2),
+             ptr(permd), ptr(d(x_pos)), ptr(out), ptr(h_save), ptr(t_save), n, st)
+    ref_out = torch.empty(n, 3, dtype=torch.float64)
+    ref_out[perm] = res.detach()
+    e_f = rel_err(out, ref_out)
+    go, gh, gX = torch.empty(n, 4, device=DEV), torch.empty(n, 16, device=DEV), torch.empty(n, 32, device=DEV)
+    lib.call("ddmp_head_bwd", kind, ptr(d(g_out)), ptr(permd), ptr(W1), ptr(W2), ptr(h_save), ptr(t_save), 0.01,
+             ptr(go), ptr(gh), ptr(gX), n, st)
+    from dual_dmp_b200 import functional as F_
+    e_x = rel_err(gX, x.grad)
+    gW1 = F_.gemm_dw(gh, Yd, 32, scale=d(scale), shift=d(shift))
+    gW2 = F_.gemm_dw(go, h_save, 16)[:3]
+    e_w = (rel_err(gW1, lin1.weight.grad), rel_err(gW2, lin2.weight.grad), rel_err(F_.colsum(gh), lin1.bias.grad),
+           rel_err(F_.colsum(go)[:3], lin2.bias.grad))
+    report(f"head kind={kind}", (e_f, e_x) + e_w)
+    assert e_f < 5e-6 and e_x < 2e-5 and max(e_w) < 5e-5, (e_f, e_x, e_w)
+
+
+def test_gcnconv_operator_level(graphs):
+    """conv(x, edge_index) drop-in for torch_geometric.nn.GCNConv: forward + all three gradients vs the oracle"""
+    from dual_dmp_b200.util.networks import GCNConv
+    from oracle.gcn_ref import GCNConvRef
+    g = graphs["open"]
+    for ei, n in ((g["ds"].edge_index, g["vg"].n), (g["ds"].face_index, g["fg"].n)):
+        for cin, cout in ((7, 32), (64, 128), (20, 12)):
+            torch.manual_seed(cin)
+            ref = GCNConvRef(cin, cout)
+            with torch.no_grad():
+                ref.bias.normal_()
+            conv = GCNConv(cin, cout).to(DEV)
+            conv.load_state_dict(ref.state_dict())
+            x = torch.randn(n, cin)
+            xr = x.clone().requires_grad_(True)
+            xd = x.to(DEV).requires_grad_(True)
+            gy = torch.randn(n, cout)
+            ref(xr, ei).backward(gy)
+            y = conv(xd, ei)
+            y.backward(gy.to(DEV))
+            errs = (rel_err(y, ref(xr, ei)), rel_err(xd.grad, xr.grad), rel_err(conv.lin.weight.grad, ref.lin.weight.grad),
+                    rel_err(conv.bias.grad, ref.bias.grad))
+            report(f"gcnconv {cin}->{cout} n={n}", errs)
+            assert max(errs) < 1e-4, errs
+
+
+def test_directed_graph_backward_uses_transpose():
+    from dual_dmp_b200.util.networks import GCNConv
+    from oracle.gcn_ref import GCNConvRef
+    torch.manual_seed(3)
+    n = 50
+    ei = torch.randint(0, n, (2, 300))
+    ref = GCNConvRef(8, 32)
+    conv = GCNConv(8, 32).to(DEV)
+    conv.load_state_dict(ref.state_dict())
+    x = torch.randn(n, 8)
+    xr, xd = x.clone().requires_grad_(True), x.to(DEV).requires_grad_(True)
+    gy = torch.randn(n, 32)
+    ref(xr, ei).backward(gy)
+    conv(xd, ei).backward(gy.to(DEV))
+    assert rel_err(xd.grad, xr.grad) < 1e-4 and rel_err(conv.lin.weight.grad, ref.lin.weight.grad) < 1e-4
