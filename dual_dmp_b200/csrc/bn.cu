@@ -7,20 +7,35 @@
 
 namespace ddmp {
 
-// One CTA = 32 channels x 8 block-lanes.  sums[s][c] (double) for c in this CTA's 32 channels.
+// One CTA = 32 channels x kFinLanes block-lanes (1024 threads).  sums[s] (double) for channel c, valid in all
+// threads; lane ty accumulates blocks ty, ty+kFinLanes, ... and the lanes are combined in lane order, so the
+// summation order is fixed.
+constexpr int kFinLanes = 32;
+constexpr int kFinThreads = 32 * kFinLanes;
 template <int SETS>
 __device__ __forceinline__ void reduce_partials(const float* __restrict__ partials, int64_t nblk, int C, int c,
                                                 double (&out)[SETS]) {
-    __shared__ double red[8][SETS][33];
+    __shared__ double red[kFinLanes][SETS][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     double acc[SETS];
 #pragma unroll
     for (int s = 0; s < SETS; ++s) acc[s] = 0.0;
     if (c < C) {
-        for (int64_t b = ty; b < nblk; b += 8) {
-            const float* p = partials + (b * SETS) * C + c;
+        int64_t b = ty;
+        for (; b + 3 * kFinLanes < nblk; b += 4 * kFinLanes) {
+            float v[4][SETS];
 #pragma unroll
-            for (int s = 0; s < SETS; ++s) acc[s] += (double)__ldg(p + (int64_t)s * C);
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int s = 0; s < SETS; ++s) v[u][s] = __ldg(partials + ((b + u * kFinLanes) * SETS + s) * C + c);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int s = 0; s < SETS; ++s) acc[s] += (double)v[u][s];
+        }
+        for (; b < nblk; b += kFinLanes) {
+#pragma unroll
+            for (int s = 0; s < SETS; ++s) acc[s] += (double)__ldg(partials + (b * SETS + s) * C + c);
         }
     }
 #pragma unroll
@@ -29,13 +44,13 @@ __device__ __forceinline__ void reduce_partials(const float* __restrict__ partia
 #pragma unroll
     for (int s = 0; s < SETS; ++s) {
         double t = 0.0;
-#pragma unroll
-        for (int y = 0; y < 8; ++y) t += red[y][s][tx];
+#pragma unroll 8
+        for (int y = 0; y < kFinLanes; ++y) t += red[y][s][tx];
         out[s] = t;
     }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kFinThreads)
 bn_stats_finalize_kernel(const float* __restrict__ partials, int64_t nblk, int64_t n, int C,
                          const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float momentum,
                          float* running_mean, float* running_var, float* mean, float* rstd, float* scale,
@@ -62,7 +77,7 @@ bn_stats_finalize_kernel(const float* __restrict__ partials, int64_t nblk, int64
     }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kFinThreads)
 bn_bwd_finalize_kernel(const float* __restrict__ partials, int64_t nblk, int64_t n, int C, float* dgamma,
                        float* dbeta, float* c1, float* c2) {
     const int c = blockIdx.x * 32 + (threadIdx.x & 31);
@@ -77,7 +92,7 @@ bn_bwd_finalize_kernel(const float* __restrict__ partials, int64_t nblk, int64_t
 }
 
 template <int SETS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kFinThreads)
 colsum_finalize_kernel(const float* __restrict__ partials, int64_t nblk, int C, float* out) {
     const int c = blockIdx.x * 32 + (threadIdx.x & 31);
     double s[SETS];
@@ -186,7 +201,7 @@ int ddmp_bn_stats_finalize(const float* partials, int64_t nblk, int64_t n, int32
     using namespace ddmp;
     DDMP_REQUIRE(partials && gamma && beta && mean && rstd && scale && shift, "bn_stats_finalize: null pointer");
     DDMP_REQUIRE(n > 0 && C > 0 && nblk > 0, "bn_stats_finalize: bad shape");
-    bn_stats_finalize_kernel<<<(unsigned)ceil_div(C, 32), 256, 0, as_stream(stream)>>>(
+    bn_stats_finalize_kernel<<<(unsigned)ceil_div(C, 32), kFinThreads, 0, as_stream(stream)>>>(
         partials, nblk, n, C, gamma, beta, eps, momentum, running_mean, running_var, mean, rstd, scale, shift);
     return check_launch("bn_stats_finalize");
 }
@@ -205,7 +220,7 @@ int ddmp_bn_bwd_finalize(const float* partials, int64_t nblk, int64_t n, int32_t
     using namespace ddmp;
     DDMP_REQUIRE(partials && dgamma && dbeta && c1 && c2, "bn_bwd_finalize: null pointer");
     DDMP_REQUIRE(n > 0 && C > 0 && nblk > 0, "bn_bwd_finalize: bad shape");
-    bn_bwd_finalize_kernel<<<(unsigned)ceil_div(C, 32), 256, 0, as_stream(stream)>>>(partials, nblk, n, C, dgamma,
+    bn_bwd_finalize_kernel<<<(unsigned)ceil_div(C, 32), kFinThreads, 0, as_stream(stream)>>>(partials, nblk, n, C, dgamma,
                                                                                     dbeta, c1, c2);
     return check_launch("bn_bwd_finalize");
 }
@@ -233,8 +248,8 @@ int ddmp_colsum_finalize(const float* partials, int64_t nblk, int32_t sets, int3
     DDMP_REQUIRE(partials && out && nblk > 0 && C > 0, "colsum_finalize: bad arguments");
     const unsigned grid = (unsigned)ceil_div(C, 32);
     cudaStream_t st = as_stream(stream);
-    if (sets == 1) colsum_finalize_kernel<1><<<grid, 256, 0, st>>>(partials, nblk, C, out);
-    else if (sets == 2) colsum_finalize_kernel<2><<<grid, 256, 0, st>>>(partials, nblk, C, out);
+    if (sets == 1) colsum_finalize_kernel<1><<<grid, kFinThreads, 0, st>>>(partials, nblk, C, out);
+    else if (sets == 2) colsum_finalize_kernel<2><<<grid, kFinThreads, 0, st>>>(partials, nblk, C, out);
     else { set_error("colsum_finalize: sets must be 1 or 2"); return DDMP_ERR_INVALID; }
     return check_launch("colsum_finalize");
 }

@@ -42,3 +42,50 @@ def report(name: str, value) -> None:
     os.makedirs(os.path.join(root, "gpurun_out"), exist_ok=True)
     with open(os.path.join(root, "gpurun_out", "parity.log"), "a") as f:
         f.write(f"{name}\t{value}\n")
+
+
+class MaskedLeaky:
+    """LeakyReLU whose active set is prescribed (one boolean mask per trunk layer, then the stock function).
+
+    fp32 implementations that agree to 1e-6 still disagree on the SIGN of a pre-activation that lies within
+    rounding of zero (about one element per network pass at these sizes); that element's slope flips 1 <-> 0.01 and
+    the gradients upstream of it move by ~1e-3.  Evaluating the float64 oracle on the product's own active set makes
+    the gradient comparison well-posed; the sign decisions themselves are covered by the activation parity check.
+    """
+
+    def __init__(self, masks, slope=0.01):
+        self.masks, self.slope, self.i = list(masks), slope, 0
+
+    def __call__(self, z):
+        if self.i < len(self.masks):
+            m = self.masks[self.i]
+            self.i += 1
+            return torch.where(m, z, z * self.slope)
+        return torch.nn.functional.leaky_relu(z, self.slope)
+
+
+def product_masks(net_d):
+    """active sets of the product's 12 trunk layers in the CALLER's node numbering (needs net_d.taps filled)."""
+    perm = torch.from_numpy(net_d.last_graph.perm_host)
+    masks = []
+    for y, st in net_d.taps:
+        z = (y * st[2] + st[3]).cpu()
+        m = torch.empty_like(z, dtype=torch.bool)
+        m[perm] = z > 0
+        masks.append(m)
+    return masks
+
+
+def oracle64_like(net_r, masks):
+    """float64 deep copy of an oracle network that uses the prescribed active sets"""
+    import copy
+    net = copy.deepcopy(net_r).double()
+    net.zero_grad()
+    net.l_relu = MaskedLeaky(masks)
+    return net
+
+
+def dataset64(ds):
+    from types import SimpleNamespace
+    return SimpleNamespace(z1=ds.z1.detach().double(), z2=ds.z2.detach().double(), x_pos=ds.x_pos.double(),
+                           x_norm=ds.x_norm.double(), edge_index=ds.edge_index, face_index=ds.face_index)

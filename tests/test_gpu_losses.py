@@ -108,8 +108,8 @@ def test_losses_against_oracle_medium(kind, n, loop):
     nrm0 = nrm0 / nrm0.norm(dim=1, keepdim=True)
 
     def run(mod, dev):
-        p = pos0.to(dev).requires_grad_(True)
-        q = nrm0.to(dev).requires_grad_(True)
+        p = pos0.clone().to(dev).requires_grad_(True)
+        q = nrm0.clone().to(dev).requires_grad_(True)
         ls = [mod.pos_rec_loss(p, n_mesh.vs), mod.mesh_laplacian_loss(p, n_mesh), mod.norm_rec_loss(q, n_mesh.fn)]
         l4, nf = mod.fn_bnf_loss(p, q, n_mesh, loop=loop)
         ls += [l4, mod.pos_norm_loss(p, q, n_mesh)]

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from tests.helpers import rel_err, report, small_case
+from tests.helpers import (dataset64, oracle64_like, product_masks, rel_err, report, small_case)
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -30,18 +30,30 @@ def _pair(seed=0):
     return pr, nr, pd, nd
 
 
-def _compare_grads(net_d, net_r, tag, tol=1e-4):
+def _compare_grads(net_d, net_x, tag, tol=1e-4):
+    """parameter gradients of the product against an oracle network (fp32 oracle, or the float64 oracle evaluated on
+    the product's own LeakyReLU active sets — see tests/helpers.MaskedLeaky)"""
     worst = 0.0
-    for (name, pd), (_, pr) in zip(net_d.named_parameters(), net_r.named_parameters()):
+    for (name, pd), (_, px) in zip(net_d.named_parameters(), net_x.named_parameters()):
         assert pd.grad is not None, name
         if name.startswith("conv") and name.endswith(".bias"):
-            floor = 1e-5 * max(1.0, float(pr.grad.abs().max()))
+            # true gradient of a bias that feeds BatchNorm is 0; both sides hold rounding noise
+            floor = 1e-5 * max(1.0, float(px.grad.abs().max()))
             assert float(pd.grad.abs().max()) < 1e-4 + floor, (name, float(pd.grad.abs().max()))
             continue
-        e = rel_err(pd.grad, pr.grad)
+        e = rel_err(pd.grad, px.grad)
         worst = max(worst, e)
         assert e < tol, (tag, name, e)
     return worst
+
+
+def _count_flips(net_d, taps_r):
+    """LeakyReLU sign disagreements between the product and the fp32 oracle (pre-activations within rounding of 0)"""
+    masks = product_masks(net_d)
+    flips = 0
+    for m, (y_r, x_r) in zip(masks, taps_r):
+        flips += int((m != (x_r > 0)).sum())
+    return flips, masks
 
 
 @pytest.mark.parametrize("kind,n", [("ico", 8), ("ico", 20), ("open", 12)])
@@ -61,6 +73,7 @@ def test_per_layer_activations_and_grads(kind, n, reorder):
         g = torch.randn(gshape, 3, generator=torch.Generator().manual_seed(5))
         out_r.backward(g)
         out_d.backward(g.to(DEV))
+        # ---- per-layer activations against the fp32 oracle ----
         worst_act = 0.0
         p = torch.from_numpy(net_d.last_graph.perm_host)          # product row i is node perm[i]
         assert (net_d.last_graph.perm is not None) == reorder
@@ -70,9 +83,14 @@ def test_per_layer_activations_and_grads(kind, n, reorder):
             worst_act = max(worst_act, e_y, e_x)
             assert e_y < 1e-4 and e_x < 1e-4, (l, e_y, e_x)
         e_out = rel_err(out_d, out_r)
-        e_g = _compare_grads(net_d, net_r, f"{kind}{n}")
-        report(f"net {type(net_d).__name__} {kind}{n} reorder={reorder}", (worst_act, e_out, e_g))
         assert e_out < 1e-4
+        # ---- gradients: float64 oracle on the product's active sets (always), fp32 oracle when no sign flipped ----
+        flips, masks = _count_flips(net_d, taps_r)
+        net_64 = oracle64_like(net_r, masks)
+        net_64(dataset64(ds)).backward(g.double())
+        e_g64 = _compare_grads(net_d, net_64, f"{kind}{n} vs oracle64")
+        e_g32 = _compare_grads(net_d, net_r, f"{kind}{n} vs oracle32") if flips == 0 else float("nan")
+        report(f"net {type(net_d).__name__} {kind}{n} reorder={reorder}", (worst_act, e_out, e_g64, e_g32, flips))
         # BatchNorm running statistics follow the reference semantics
         for i in (1, 6, 12):
             assert rel_err(getattr(net_d, f"bn{i}").running_mean, getattr(net_r, f"bn{i}").running_mean) < 1e-4
@@ -95,9 +113,12 @@ def test_full_step_losses_and_gradients(cfg):
     for it in range(3):
         for o in opt_r + opt_d:
             o.zero_grad()
+        taps_p, taps_n = [], []
+        pr.train(); nr.train()
         tot_r, parts_r, _, _ = step_ref.losses(pr, nr, ds, n_mesh, k, cfg["loop"], epoch=101)
         tot_r.backward()
         pd.train(); nd.train()
+        pd.taps, nd.taps = [], []
         pos = pd(ds)
         l1 = L.pos_rec_loss(pos, n_mesh.vs)
         l2 = L.mesh_laplacian_loss(pos, n_mesh)
@@ -110,13 +131,18 @@ def test_full_step_losses_and_gradients(cfg):
         parts_d = [x.item() for x in (l1, l2, l3, l4, l5)]
         e_l = max(abs(a - b.item()) / (abs(b.item()) + 1e-9) for a, b in zip(parts_d, parts_r))
         if it == 0:
-            e_gp = _compare_grads(pd, pr, "posnet step", tol=2e-4)
-            e_gn = _compare_grads(nd, nr, "normnet step", tol=2e-4)
-            report(f"step k={k} loop={cfg['loop']}", (e_l, e_gp, e_gn))
             assert e_l < 1e-4, (parts_d, [p.item() for p in parts_r])
+            # gradients of the whole step: float64 oracle evaluated on the product's LeakyReLU active sets
+            p64 = oracle64_like(pr, product_masks(pd))
+            n64 = oracle64_like(nr, product_masks(nd))
+            tot64, _, _, _ = step_ref.losses(p64, n64, dataset64(ds), n_mesh, k, cfg["loop"], epoch=101)
+            tot64.backward()
+            e_gp = _compare_grads(pd, p64, "posnet step")
+            e_gn = _compare_grads(nd, n64, "normnet step")
+            report(f"step k={k} loop={cfg['loop']}", (e_l, e_gp, e_gn))
         else:
-            # Adam amplifies rounding noise of near-zero gradients (sign-like update), so later iterations are
-            # only required to track the oracle loosely
+            # Adam turns rounding noise of near-zero gradients into +-lr steps (sign-like update), so later
+            # iterations are only required to track the oracle loosely
             assert e_l < 5e-2, (it, parts_d, [p.item() for p in parts_r])
         for net in (nr, nd):
             torch.nn.utils.clip_grad_norm_(net.parameters(), 0.8)
