@@ -1,0 +1,359 @@
+// Dense feature transform on the 5th-generation tensor cores (DDMP_GEMM_TC): tcgen05.mma kind::tf32 with an
+// error-compensated 3xTF32 split (hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM), so the result keeps fp32-level
+// accuracy (the 1e-4 parity contract rules out plain TF32, SURVEY.md §7 hard part 1).
+//
+//   NT kernel (xw, dx):  C[M=rows, N] = act(A)[rows, K] * B[N, K]^T        A, B K-major
+//   TN kernel (dw)    :  C[M, N] = sum_rows A[rows, M]^T * act(B)[rows, N]  A, B MN-major, split-K over rows
+//
+// The A/B operands cannot come straight from TMA: the activation (previous layer's BatchNorm + LeakyReLU) and the
+// hi/lo split are applied while the tile is staged, so 8 producer warps do   ld.global -> transform -> st.shared
+// into the 128-byte-swizzled UMMA canonical layout, one elected thread of a 9th warp issues the MMAs, and all
+// producer warps drain the TMEM accumulator in the epilogue.  Pipeline: `full`/`empty` mbarriers per smem stage,
+// tcgen05.commit releases a stage / publishes the accumulator.
+#include "common.cuh"
+
+namespace ddmp {
+namespace tc {
+
+constexpr int kProducerWarps = 8;
+constexpr int kProducerThreads = kProducerWarps * 32;
+constexpr int kThreads = kProducerThreads + 32;      // + MMA warp
+constexpr int BM = 128;                              // UMMA M
+constexpr int BK = 32;                               // 32 fp32 = 128 bytes = one swizzle atom row
+constexpr int UMMA_K = 8;                            // kind::tf32
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra.uni WAIT_DONE;\n"
+        "bra.uni WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// tf32 split: hi = rna(x), lo = rna(x - hi)
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+    const float r = x - __uint_as_float(hi);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+
+// ---- descriptors ----------------------------------------------------------------------------------------------------
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) |
+// version=1 [46,48) | layout_type [61,64) (2 = SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor) for kind::tf32, fp32 accumulate
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_mn_major, bool b_mn_major) {
+    return (1u << 4)                       // c_format = F32
+           | (2u << 7) | (2u << 10)        // a_format = b_format = TF32
+           | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) |
+           ((uint32_t)(M >> 4) << 24);
+}
+
+// byte offset of (row r, 16-byte chunk c) inside a K-major SWIZZLE_128B tile whose rows are 128 bytes
+__device__ __forceinline__ uint32_t sw128(uint32_t r, uint32_t c) { return r * 128u + ((c ^ (r & 7u)) << 4); }
+
+struct NtArgs {
+    const float* A;       // [*, K] row-major; row m of the tile is A[map ? map[m] : m]
+    const float* B;       // [N, K] row-major
+    float* C;             // [M, N]
+    const int* a_map;
+    const float* scale;   // act over k (A operand) when non-null
+    const float* shift;
+    float slope;
+    int64_t M;
+    int N, K;
+    int tiles_n;
+};
+
+// ---- NT kernel ------------------------------------------------------------------------------------------------------
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kThreads, 1) tc_gemm_nt_kernel(const NtArgs g) {
+    constexpr uint32_t A_BYTES = BM * 128;           // one of hi / lo
+    constexpr uint32_t B_BYTES = BN * 128;
+    constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // carve: stages (1024-aligned), then barriers
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* accum_bar = empty_bar + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tn = blockIdx.x % g.tiles_n;
+    const int64_t m0 = (int64_t)(blockIdx.x / g.tiles_n) * BM;
+    const int n0 = tn * BN;
+    const int num_kb = g.K / BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar + s, kProducerWarps);
+            mbar_init(empty_bar + s, 1);
+        }
+        mbar_init(accum_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == kProducerWarps) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < kProducerWarps) {
+        // ===== producers: global -> (act, split) -> swizzled smem =====
+        const int t = threadIdx.x;               // 0..255
+        const uint32_t c = t & 7;                // 16-byte chunk along K owned by this thread
+        const bool has_act = g.scale != nullptr;
+        for (int kb = 0; kb < num_kb; ++kb) {
+            const int s = kb % STAGES;
+            const uint32_t ph = (kb / STAGES) & 1;
+            const int k0 = kb * BK + c * 4;
+            // issue the global loads before waiting for the slot
+            float4 av[BM * 8 / kProducerThreads];
+#pragma unroll
+            for (int j = 0; j < BM * 8 / kProducerThreads; ++j) {
+                const int row = (t >> 3) + j * (kProducerThreads / 8);
+                const int64_t m = m0 + row;
+                if (m < g.M) {
+                    const int64_t src = g.a_map ? (int64_t)__ldg(g.a_map + m) : m;
+                    av[j] = ldg4(g.A + src * g.K + k0);
+                } else {
+                    av[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+            float4 bv[BN * 8 / kProducerThreads];
+#pragma unroll
+            for (int j = 0; j < BN * 8 / kProducerThreads; ++j) {
+                const int row = (t >> 3) + j * (kProducerThreads / 8);
+                bv[j] = ldg4(g.B + (int64_t)(n0 + row) * g.K + k0);
+            }
+            float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (has_act) { sc = ldg4(g.scale + k0); sh = ldg4(g.shift + k0); }
+
+            mbar_wait(empty_bar + s, ph ^ 1u);
+            uint8_t* st = smem + s * STAGE_BYTES;
+#pragma unroll
+            for (int j = 0; j < BM * 8 / kProducerThreads; ++j) {
+                const uint32_t row = (t >> 3) + j * (kProducerThreads / 8);
+                float4 a = av[j];
+                if (has_act && (m0 + row) < g.M) {
+                    a.x = lrelu(fmaf(a.x, sc.x, sh.x), g.slope); a.y = lrelu(fmaf(a.y, sc.y, sh.y), g.slope);
+                    a.z = lrelu(fmaf(a.z, sc.z, sh.z), g.slope); a.w = lrelu(fmaf(a.w, sc.w, sh.w), g.slope);
+                }
+                uint4 hi, lo;
+                split_tf32(a.x, hi.x, lo.x); split_tf32(a.y, hi.y, lo.y);
+                split_tf32(a.z, hi.z, lo.z); split_tf32(a.w, hi.w, lo.w);
+                const uint32_t off = sw128(row, c);
+                *reinterpret_cast<uint4*>(st + off) = hi;
+                *reinterpret_cast<uint4*>(st + A_BYTES + off) = lo;
+            }
+#pragma unroll
+            for (int j = 0; j < BN * 8 / kProducerThreads; ++j) {
+                const uint32_t row = (t >> 3) + j * (kProducerThreads / 8);
+                const float4 b = bv[j];
+                uint4 hi, lo;
+                split_tf32(b.x, hi.x, lo.x); split_tf32(b.y, hi.y, lo.y);
+                split_tf32(b.z, hi.z, lo.z); split_tf32(b.w, hi.w, lo.w);
+                const uint32_t off = sw128(row, c);
+                *reinterpret_cast<uint4*>(st + 2 * A_BYTES + off) = hi;
+                *reinterpret_cast<uint4*>(st + 2 * A_BYTES + B_BYTES + off) = lo;
+            }
+            fence_proxy_async();                 // make the generic-proxy stores visible to the tensor-core proxy
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full_bar + s);
+        }
+
+        // ===== epilogue: TMEM -> registers -> global =====
+        mbar_wait(accum_bar, 0);
+        tc_fence_after();
+        const int q = warp & 3;                  // TMEM lane quarter this warp may access
+        const int half = warp >> 2;              // column half
+        const int64_t m = m0 + q * 32 + lane;
+#pragma unroll 1
+        for (int cb = half * (BN / 2); cb < (half + 1) * (BN / 2); cb += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, v);
+            if (m < g.M) {
+                float* dst = g.C + m * g.N + n0 + cb;
+#pragma unroll
+                for (int e = 0; e < 32; e += 4)
+                    st4(dst + e, make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]),
+                                             __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3])));
+            }
+        }
+        tc_fence_before();
+    } else {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BM, BN, false, false);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(full_bar + s, ph);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+#pragma unroll
+                for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+                    const uint32_t koff = ks * UMMA_K * 4;       // bytes along K inside the swizzle atom
+                    const uint64_t a_hi = make_desc(sa + koff, 16, 1024);
+                    const uint64_t a_lo = make_desc(sa + A_BYTES + koff, 16, 1024);
+                    const uint64_t b_hi = make_desc(sa + 2 * A_BYTES + koff, 16, 1024);
+                    const uint64_t b_lo = make_desc(sa + 2 * A_BYTES + B_BYTES + koff, 16, 1024);
+                    umma_tf32(tmem_base, a_lo, b_hi, idesc, (kb | ks) != 0);
+                    umma_tf32(tmem_base, a_hi, b_lo, idesc, 1);
+                    umma_tf32(tmem_base, a_hi, b_hi, idesc, 1);
+                }
+                umma_commit(empty_bar + s);      // frees the smem stage when these MMAs retire
+            }
+            umma_commit(accum_bar);              // accumulator complete
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    if (warp == kProducerWarps) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+template <int BN, int STAGES>
+static int launch_nt(const NtArgs& g, cudaStream_t st) {
+    constexpr size_t smem = (size_t)STAGES * (2 * BM * 128 + 2 * BN * 128) + 1024 + 256;
+    static bool configured = false;
+    if (!configured) {
+        DDMP_CUDA(cudaFuncSetAttribute(tc_gemm_nt_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+        configured = true;
+    }
+    const int64_t tiles = ceil_div(g.M, BM) * g.tiles_n;
+    DDMP_REQUIRE(tiles < (1ll << 31), "tc gemm: too many tiles");
+    tc_gemm_nt_kernel<BN, STAGES><<<(unsigned)tiles, kThreads, smem, st>>>(g);
+    return check_launch("tc_gemm_nt");
+}
+
+static int run_nt(const float* A, const int* a_map, const float* scale, const float* shift, float slope,
+                  const float* B, float* C, int64_t M, int N, int K, cudaStream_t st) {
+    NtArgs g{};
+    g.A = A; g.B = B; g.C = C; g.a_map = a_map; g.scale = scale; g.shift = shift; g.slope = slope;
+    g.M = M; g.N = N; g.K = K;
+    if (N % 256 == 0) { g.tiles_n = N / 256; return launch_nt<256, 2>(g, st); }
+    if (N % 128 == 0) { g.tiles_n = N / 128; return launch_nt<128, 3>(g, st); }
+    g.tiles_n = N / 64;
+    return launch_nt<64, 4>(g, st);
+}
+
+__global__ void transpose_kernel(const float* __restrict__ W, float* __restrict__ Wt, int rows, int cols) {
+    __shared__ float tile[32][33];
+    const int x = blockIdx.x * 32 + threadIdx.x, y0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y)
+        if (x < cols && y0 + j < rows) tile[j][threadIdx.x] = W[(int64_t)(y0 + j) * cols + x];
+    __syncthreads();
+    const int xt = blockIdx.y * 32 + threadIdx.x, yt0 = blockIdx.x * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y)
+        if (xt < rows && yt0 + j < cols) Wt[(int64_t)(yt0 + j) * rows + xt] = tile[threadIdx.x][j];
+}
+
+}  // namespace tc
+
+static inline bool tc_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+bool tc_supported_xw(int64_t n, int32_t Cin, int32_t Cout) {
+    return n > 0 && Cin >= 64 && Cout >= 64 && Cin % 32 == 0 && Cout % 64 == 0 && Cout <= 4096;
+}
+bool tc_supported_dx(int64_t n, int32_t Cin, int32_t Cout) {
+    return n > 0 && Cin >= 64 && Cout >= 64 && Cout % 32 == 0 && Cin % 64 == 0 && Cin <= 4096;
+}
+bool tc_supported_dw(int64_t, int32_t, int32_t) { return false; }
+
+int tc_gemm_xw(const float* X, const int32_t* row_map, const float* scale, const float* shift, float slope,
+               const float* W, float* H, int64_t n, int32_t Cin, int32_t Cout, cudaStream_t st) {
+    DDMP_REQUIRE(tc_aligned16(X) && tc_aligned16(W) && tc_aligned16(H), "tc_gemm_xw: pointers must be 16-byte aligned");
+    return tc::run_nt(X, row_map, scale, shift, slope, W, H, n, Cout, Cin, st);
+}
+
+// gX[n,Cin] = dH[n,Cout] * W[Cout,Cin]: the B operand must be K-major, i.e. Wt = W^T [Cin, Cout] (ddmp_transpose).
+int tc_gemm_dx(const float* dH, const float* Wt, float* gX, int64_t n, int32_t Cin, int32_t Cout, cudaStream_t st) {
+    DDMP_REQUIRE(Wt != nullptr, "tc_gemm_dx: needs the transposed weights Wt");
+    DDMP_REQUIRE(tc_aligned16(dH) && tc_aligned16(Wt) && tc_aligned16(gX), "tc_gemm_dx: pointers must be 16-byte aligned");
+    return tc::run_nt(dH, nullptr, nullptr, nullptr, 0.f, Wt, gX, n, Cin, Cout, st);
+}
+
+int transpose(const float* src, float* dst, int32_t rows, int32_t cols, cudaStream_t st) {
+    dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)ceil_div(rows, 32));
+    tc::transpose_kernel<<<grid, dim3(32, 8), 0, st>>>(src, dst, rows, cols);
+    return check_launch("transpose");
+}
+
+int64_t tc_gemm_dw_workspace_bytes(int64_t, int32_t, int32_t) { return 0; }
+int tc_gemm_dw(const float*, const float*, const int32_t*, const float*, const float*, float, float*, void*, int64_t,
+               int64_t, int32_t, int32_t, cudaStream_t) {
+    set_error("tc_gemm_dw: not available");
+    return DDMP_ERR_UNSUPPORTED;
+}
+
+}  // namespace ddmp

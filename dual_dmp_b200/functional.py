@@ -54,8 +54,12 @@ def gemm_dx(dH, W, out=None, backend=None):
     n = dH.shape[0]
     Cout, Cin = W.shape
     gX = out if out is not None else torch.empty(n, Cin, dtype=torch.float32, device=dH.device)
-    lib.call("ddmp_gemm_dx", ptr(dH), ptr(W), ptr(gX), n, Cin, Cout, GEMM_BACKEND if backend is None else backend,
-             stream_ptr(dH.device))
+    backend = GEMM_BACKEND if backend is None else backend
+    Wt = None
+    if backend != 1 and min(Cin, Cout) >= 64:          # the tensor-core path reads W^T (K-major B operand)
+        Wt = torch.empty(Cin, Cout, dtype=torch.float32, device=dH.device)
+        lib.call("ddmp_transpose", ptr(W), ptr(Wt), Cout, Cin, stream_ptr(dH.device))
+    lib.call("ddmp_gemm_dx", ptr(dH), ptr(W), ptr(Wt), ptr(gX), n, Cin, Cout, backend, stream_ptr(dH.device))
     return gX
 
 

@@ -18,8 +18,16 @@ raises ``ValueError``).
 """
 from __future__ import annotations
 
+import warnings
+
 import numpy as np
 import torch
+
+
+def _coo(inds, vals, size):
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")          # "Sparse invariant checks are implicitly disabled"
+        return torch.sparse_coo_tensor(inds, vals, size=size, check_invariants=False)
 
 
 class Mesh:
@@ -111,7 +119,7 @@ class Mesh:
         v2v_inds = torch.from_numpy(np.concatenate([v2v_inds, v2v_inds[[1, 0]]], axis=1)).long()
         v2v_vals = torch.ones(v2v_inds.shape[1]).float()
         nv = len(self.vs)
-        self.v2v_mat = torch.sparse_coo_tensor(v2v_inds, v2v_vals, size=(nv, nv))
+        self.v2v_mat = _coo(v2v_inds, v2v_vals, (nv, nv))
         self.v_dims = torch.from_numpy(
             np.bincount(self.edges.reshape(-1).astype(np.int64), minlength=nv).astype(np.float32))
 
@@ -172,7 +180,7 @@ class Mesh:
     def v2f_mat(self):
         rows = np.repeat(np.arange(len(self.vs), dtype=np.int64), np.diff(self.vf_ptr))
         inds = torch.from_numpy(np.stack([rows, self.vf_idx]))
-        return torch.sparse_coo_tensor(inds, torch.ones(inds.shape[1]), size=(len(self.vs), len(self.faces)))
+        return _coo(inds, torch.ones(inds.shape[1]), (len(self.vs), len(self.faces)))
 
     # ---- writers (reference :267-285) -------------------------------------------------------------------
     def save(self, filename):

@@ -44,7 +44,7 @@ def report(name: str, value) -> None:
         f.write(f"{name}\t{value}\n")
 
 
-class MaskedLeaky:
+class MaskedLeaky(torch.nn.Module):
     """LeakyReLU whose active set is prescribed (one boolean mask per trunk layer, then the stock function).
 
     fp32 implementations that agree to 1e-6 still disagree on the SIGN of a pre-activation that lies within
@@ -54,9 +54,10 @@ class MaskedLeaky:
     """
 
     def __init__(self, masks, slope=0.01):
+        super().__init__()
         self.masks, self.slope, self.i = list(masks), slope, 0
 
-    def __call__(self, z):
+    def forward(self, z):
         if self.i < len(self.masks):
             m = self.masks[self.i]
             self.i += 1

@@ -263,3 +263,34 @@ def test_directed_graph_backward_uses_transpose():
     ref(xr, ei).backward(gy)
     conv(xd, ei).backward(gy.to(DEV))
     assert rel_err(xd.grad, xr.grad) < 1e-4 and rel_err(conv.lin.weight.grad, ref.lin.weight.grad) < 1e-4
+
+
+TC_SHAPES = [(64, 64), (64, 128), (128, 256), (256, 512), (512, 512), (512, 256), (256, 64), (128, 64)]
+
+
+@pytest.mark.parametrize("cin,cout", TC_SHAPES)
+@pytest.mark.parametrize("n", [640, 1000, 4099])
+def test_gemm_tcgen05_3xtf32(cin, cout, n):
+    """tcgen05 kind::tf32 path with the hi/lo split: fp32-level accuracy against a float64 evaluation"""
+    from dual_dmp_b200 import functional as F_
+    torch.manual_seed(cin * 1000 + cout + n)
+    X = torch.randn(n + 5, cin)
+    W = torch.randn(cout, cin) / cin ** 0.5
+    scale, shift = torch.rand(cin) + 0.5, torch.randn(cin)
+    rmap = torch.randperm(n + 5)[:n].to(torch.int32)
+    dH = torch.randn(n, cout)
+    Xd, Wd, dHd = X.to(DEV), W.to(DEV), dH.to(DEV)
+    sc, sh, rm = scale.to(DEV), shift.to(DEV), rmap.to(DEV)
+    Xn = Xd[:n].contiguous()
+    act = torch.nn.functional.leaky_relu(X.double() * scale.double() + shift.double(), 0.01)
+    e1 = rel_err(F_.gemm_xw(Xn, Wd, backend=2), X[:n].double() @ W.double().t())
+    e2 = rel_err(F_.gemm_xw(Xn, Wd, scale=sc, shift=sh, backend=2), act[:n] @ W.double().t())
+    e3 = rel_err(F_.gemm_xw(Xd, Wd, row_map=rm, n=n, backend=2), X[rmap.long()].double() @ W.double().t())
+    e4 = rel_err(F_.gemm_dx(dHd, Wd, backend=2), dH.double() @ W.double())
+    report(f"gemm_tc cin={cin} cout={cout} n={n}", (e1, e2, e3, e4))
+    assert max(e1, e2, e3, e4) < 5e-6, (e1, e2, e3, e4)
+    a = F_.gemm_xw(Xn, Wd, scale=sc, shift=sh, backend=2)
+    b = F_.gemm_xw(Xn, Wd, scale=sc, shift=sh, backend=2)
+    assert torch.equal(a, b)
+    # and it agrees with the FFMA kernel to fp32 rounding
+    assert rel_err(a, F_.gemm_xw(Xn, Wd, scale=sc, shift=sh, backend=1)) < 5e-6
