@@ -307,6 +307,214 @@ static int run_nt(const float* A, const int* a_map, const float* scale, const fl
     return launch_nt<64, 4>(g, st);
 }
 
+// ---- TN kernel (dW) -------------------------------------------------------------------------------------------------
+// dW[M=Cout, N=Cin] = sum over rows r of A[r, m] * act(B)[r, n].  Both operands are MN-major: a K index is a graph
+// row, and a row of dH / X is contiguous along the channel.  SWIZZLE_128B MN-major canonical layout (CUTLASS
+// mma_traits_sm100.hpp "make_umma_desc<Major::MN>"): element (mn, k) of a stage lives at
+//     (mn/32)*LBO + (k/8)*1024 + (k%8)*128 + ((((mn%32)/4) ^ (k%8)) * 16) + (mn%4)*4
+// Work item = (row segment of kSegRows rows, output tile); items are dealt round-robin to persistent CTAs with the
+// tile index fastest, so CTAs running together read the same rows (L2 reuse).  Every item writes its own partial
+// tile; a fixed-order float64 reduction sums the segments (deterministic, and it bounds the fp32 accumulation
+// length inside TMEM to kSegRows).
+constexpr int kSegRows = 8192;
+
+struct TnArgs {
+    const float* A;       // dH [rows, M] row-major
+    const float* B;       // X  [rows, N] row-major (pre-BatchNorm), act over n when scale != null
+    float* P;             // partials [num_seg][M][N]
+    const float* scale;
+    const float* shift;
+    float slope;
+    int64_t rows;
+    int M, N;
+    int tiles_m, tiles_n;
+    int64_t num_items;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kThreads, 1) tc_gemm_tn_kernel(const TnArgs g) {
+    constexpr uint32_t A_BYTES = BM * 128;           // 32 k-rows x 128 m x 4 B
+    constexpr uint32_t B_BYTES = BN * 128;
+    constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+    constexpr uint32_t LBO = (BK / 8) * 1024;        // next 32-wide MN block (layout [mn_blk][k_grp][8][128B])
+    constexpr int A_CH = BM / 4, B_CH = BN / 4;      // 16-byte chunks per k-row
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* accum_bar = empty_bar + STAGES;        // MMA -> epilogue: accumulator of this item complete
+    uint64_t* drained_bar = accum_bar + 1;           // epilogue -> MMA: TMEM may be overwritten
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(drained_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar + s, kProducerWarps);
+            mbar_init(empty_bar + s, 1);
+        }
+        mbar_init(accum_bar, 1);
+        mbar_init(drained_bar, kProducerWarps);
+        fence_barrier_init();
+    }
+    if (warp == kProducerWarps) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int tiles = g.tiles_m * g.tiles_n;
+
+    uint32_t it = 0;                                 // pipeline iteration counter, runs across items
+    uint32_t item_no = 0;
+    for (int64_t item = blockIdx.x; item < g.num_items; item += gridDim.x, ++item_no) {
+        const int tile = (int)(item % tiles);
+        const int64_t seg = item / tiles;
+        const int m0 = (tile / g.tiles_n) * BM, n0 = (tile % g.tiles_n) * BN;
+        const int64_t r0 = seg * kSegRows;
+        const int64_t r1 = (r0 + kSegRows < g.rows) ? (r0 + kSegRows) : g.rows;
+        const int num_kb = (int)((r1 - r0 + BK - 1) / BK);
+
+        if (warp < kProducerWarps) {
+            const int t = threadIdx.x;
+            // A: 32 chunks per k-row (BM=128) -> 8 k-rows per pass of 256 threads; B: B_CH chunks per k-row
+            const uint32_t a_cm = t % A_CH, a_r = t / A_CH;                    // a_r in [0, 256/A_CH)
+            const uint32_t b_cm = t % B_CH, b_r = t / B_CH;
+            constexpr int A_PASS = kProducerThreads / A_CH, B_PASS = kProducerThreads / B_CH;
+            const bool a_ok = (m0 + (int)a_cm * 4) < g.M;
+            const bool has_act = g.scale != nullptr;
+            float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (has_act) { sc = ldg4(g.scale + n0 + b_cm * 4); sh = ldg4(g.shift + n0 + b_cm * 4); }
+            const uint32_t a_off0 = (a_cm / 8) * LBO, b_off0 = (b_cm / 8) * LBO;
+            for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                const int64_t rb = r0 + (int64_t)kb * BK;
+                float4 av[BK / A_PASS], bv[BK / B_PASS];
+#pragma unroll
+                for (int j = 0; j < BK / A_PASS; ++j) {
+                    const int64_t r = rb + a_r + j * A_PASS;
+                    av[j] = (r < r1 && a_ok) ? ldg4(g.A + r * g.M + m0 + a_cm * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int j = 0; j < BK / B_PASS; ++j) {
+                    const int64_t r = rb + b_r + j * B_PASS;
+                    bv[j] = (r < r1) ? ldg4(g.B + r * g.N + n0 + b_cm * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                mbar_wait(empty_bar + s, ph ^ 1u);
+                uint8_t* st = smem + s * STAGE_BYTES;
+#pragma unroll
+                for (int j = 0; j < BK / A_PASS; ++j) {
+                    const uint32_t k = a_r + j * A_PASS;                        // k-row inside the stage
+                    uint4 hi, lo;
+                    split_tf32(av[j].x, hi.x, lo.x); split_tf32(av[j].y, hi.y, lo.y);
+                    split_tf32(av[j].z, hi.z, lo.z); split_tf32(av[j].w, hi.w, lo.w);
+                    const uint32_t off = a_off0 + (k >> 3) * 1024u + (k & 7u) * 128u + (((a_cm & 7u) ^ (k & 7u)) << 4);
+                    *reinterpret_cast<uint4*>(st + off) = hi;
+                    *reinterpret_cast<uint4*>(st + A_BYTES + off) = lo;
+                }
+#pragma unroll
+                for (int j = 0; j < BK / B_PASS; ++j) {
+                    const uint32_t k = b_r + j * B_PASS;
+                    float4 b = bv[j];
+                    if (has_act && (rb + k) < r1) {
+                        b.x = lrelu(fmaf(b.x, sc.x, sh.x), g.slope); b.y = lrelu(fmaf(b.y, sc.y, sh.y), g.slope);
+                        b.z = lrelu(fmaf(b.z, sc.z, sh.z), g.slope); b.w = lrelu(fmaf(b.w, sc.w, sh.w), g.slope);
+                    }
+                    uint4 hi, lo;
+                    split_tf32(b.x, hi.x, lo.x); split_tf32(b.y, hi.y, lo.y);
+                    split_tf32(b.z, hi.z, lo.z); split_tf32(b.w, hi.w, lo.w);
+                    const uint32_t off = b_off0 + (k >> 3) * 1024u + (k & 7u) * 128u + (((b_cm & 7u) ^ (k & 7u)) << 4);
+                    *reinterpret_cast<uint4*>(st + 2 * A_BYTES + off) = hi;
+                    *reinterpret_cast<uint4*>(st + 2 * A_BYTES + B_BYTES + off) = lo;
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full_bar + s);
+            }
+            // ---- epilogue of this item ----
+            mbar_wait(accum_bar, item_no & 1u);
+            tc_fence_after();
+            const int q = warp & 3, half = warp >> 2;
+            const int m = m0 + q * 32 + lane;
+            float* prow = g.P + (seg * g.M + m) * (int64_t)g.N + n0;
+#pragma unroll 1
+            for (int cb = half * (BN / 2); cb < (half + 1) * (BN / 2); cb += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, v);
+                if (m < g.M) {
+#pragma unroll
+                    for (int e = 0; e < 32; e += 4)
+                        st4(prow + cb + e, make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]),
+                                                       __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3])));
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(drained_bar);
+        } else {
+            if (lane == 0) {
+                constexpr uint32_t idesc = make_idesc(BM, BN, true, true);
+                if (item_no > 0) {                    // wait until the previous item's accumulator has been read out
+                    mbar_wait(drained_bar, (item_no - 1) & 1u);
+                    tc_fence_after();
+                }
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(full_bar + s, ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+#pragma unroll
+                    for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+                        const uint32_t koff = ks * 1024u;                       // next group of 8 k-rows
+                        const uint64_t a_hi = make_desc(sa + koff, LBO, 1024);
+                        const uint64_t a_lo = make_desc(sa + A_BYTES + koff, LBO, 1024);
+                        const uint64_t b_hi = make_desc(sa + 2 * A_BYTES + koff, LBO, 1024);
+                        const uint64_t b_lo = make_desc(sa + 2 * A_BYTES + B_BYTES + koff, LBO, 1024);
+                        umma_tf32(tmem_base, a_lo, b_hi, idesc, (kb | ks) != 0);
+                        umma_tf32(tmem_base, a_hi, b_lo, idesc, 1);
+                        umma_tf32(tmem_base, a_hi, b_hi, idesc, 1);
+                    }
+                    umma_commit(empty_bar + s);
+                }
+                umma_commit(accum_bar);
+            } else {
+                it += num_kb;
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    if (warp == kProducerWarps) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// out[i] = sum_seg partials[seg][i] in segment order, float64 accumulate
+__global__ void seg_reduce_kernel(const float* __restrict__ partials, float* __restrict__ out, int64_t count,
+                                  int64_t segs) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    double s = 0.0;
+    for (int64_t z = 0; z < segs; ++z) s += (double)__ldg(partials + z * count + i);
+    out[i] = (float)s;
+}
+
+template <int BN, int STAGES>
+static int launch_tn(const TnArgs& g, cudaStream_t st) {
+    constexpr size_t smem = (size_t)STAGES * (2 * BM * 128 + 2 * BN * 128) + 1024 + 256;
+    static bool configured = false;
+    if (!configured) {
+        DDMP_CUDA(cudaFuncSetAttribute(tc_gemm_tn_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+        configured = true;
+    }
+    const int64_t grid = g.num_items < kNumSMs ? g.num_items : kNumSMs;
+    tc_gemm_tn_kernel<BN, STAGES><<<(unsigned)grid, kThreads, smem, st>>>(g);
+    return check_launch("tc_gemm_tn");
+}
+
 __global__ void transpose_kernel(const float* __restrict__ W, float* __restrict__ Wt, int rows, int cols) {
     __shared__ float tile[32][33];
     const int x = blockIdx.x * 32 + threadIdx.x, y0 = blockIdx.y * 32;
@@ -328,7 +536,9 @@ bool tc_supported_xw(int64_t n, int32_t Cin, int32_t Cout) {
 bool tc_supported_dx(int64_t n, int32_t Cin, int32_t Cout) {
     return n > 0 && Cin >= 64 && Cout >= 64 && Cout % 32 == 0 && Cin % 64 == 0 && Cin <= 4096;
 }
-bool tc_supported_dw(int64_t, int32_t, int32_t) { return false; }
+bool tc_supported_dw(int64_t n, int32_t Cin, int32_t Cout) {
+    return n > 0 && Cin >= 64 && Cout >= 64 && Cin % 64 == 0 && Cout % 4 == 0 && Cin <= 4096 && Cout <= 4096;
+}
 
 int tc_gemm_xw(const float* X, const int32_t* row_map, const float* scale, const float* shift, float slope,
                const float* W, float* H, int64_t n, int32_t Cin, int32_t Cout, cudaStream_t st) {
@@ -349,11 +559,30 @@ int transpose(const float* src, float* dst, int32_t rows, int32_t cols, cudaStre
     return check_launch("transpose");
 }
 
-int64_t tc_gemm_dw_workspace_bytes(int64_t, int32_t, int32_t) { return 0; }
-int tc_gemm_dw(const float*, const float*, const int32_t*, const float*, const float*, float, float*, void*, int64_t,
-               int64_t, int32_t, int32_t, cudaStream_t) {
-    set_error("tc_gemm_dw: not available");
-    return DDMP_ERR_UNSUPPORTED;
+int64_t tc_gemm_dw_workspace_bytes(int64_t n, int32_t Cin, int32_t Cout) {
+    return ceil_div(n, tc::kSegRows) * (int64_t)Cin * Cout * (int64_t)sizeof(float);
+}
+
+int tc_gemm_dw(const float* dH, const float* X, const int32_t* row_map, const float* scale, const float* shift,
+               float slope, float* dW, void* workspace, int64_t workspace_bytes, int64_t n, int32_t Cin, int32_t Cout,
+               cudaStream_t st) {
+    DDMP_REQUIRE(row_map == nullptr, "tc_gemm_dw: row_map is only supported by the FFMA path");
+    DDMP_REQUIRE(workspace && workspace_bytes >= tc_gemm_dw_workspace_bytes(n, Cin, Cout),
+                 "tc_gemm_dw: workspace too small (%lld bytes)", (long long)workspace_bytes);
+    DDMP_REQUIRE(tc_aligned16(dH) && tc_aligned16(X) && tc_aligned16(workspace), "tc_gemm_dw: 16-byte alignment");
+    tc::TnArgs g{};
+    g.A = dH; g.B = X; g.P = reinterpret_cast<float*>(workspace); g.scale = scale; g.shift = shift; g.slope = slope;
+    g.rows = n; g.M = Cout; g.N = Cin;
+    g.tiles_m = (int)ceil_div(Cout, tc::BM);
+    const int64_t segs = ceil_div(n, tc::kSegRows);
+    int rc;
+    if (Cin % 256 == 0) { g.tiles_n = Cin / 256; g.num_items = segs * g.tiles_m * g.tiles_n; rc = tc::launch_tn<256, 2>(g, st); }
+    else if (Cin % 128 == 0) { g.tiles_n = Cin / 128; g.num_items = segs * g.tiles_m * g.tiles_n; rc = tc::launch_tn<128, 3>(g, st); }
+    else { g.tiles_n = Cin / 64; g.num_items = segs * g.tiles_m * g.tiles_n; rc = tc::launch_tn<64, 4>(g, st); }
+    if (rc) return rc;
+    const int64_t count = (int64_t)Cin * Cout;
+    tc::seg_reduce_kernel<<<(unsigned)ceil_div(count, 256), 256, 0, st>>>(g.P, dW, count, segs);
+    return check_launch("tc seg_reduce");
 }
 
 }  // namespace ddmp

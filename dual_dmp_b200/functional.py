@@ -149,7 +149,7 @@ class GcnNetFunction(torch.autograd.Function):
 
     params = [W_1, b_1, gamma_1, beta_1, ..., W_12, b_12, gamma_12, beta_12, W_lin1, b_lin1, W_lin2, b_lin2]
     bn_buffers = [(running_mean_l, running_var_l)] updated in place (training) or read (eval).
-    taps: optional list that receives (Y_l, stats_l) per layer for the per-layer parity tests.
+    taps: optional list that receives (Y_l, stats_l) per layer, then (h_head, None), for the per-layer parity tests.
     """
 
     @staticmethod
@@ -196,6 +196,8 @@ class GcnNetFunction(torch.autograd.Function):
         xp = _f32(x_pos, "x_pos") if kind == HEAD_POS else None
         lib.call("ddmp_head_fwd", kind, ptr(Ys[-1]), ptr(stats[-1][2]), ptr(stats[-1][3]), SLOPE, ptr(W1), ptr(b1),
                  ptr(W2), ptr(b2), ptr(graph.perm), ptr(xp), ptr(out), ptr(h_save), ptr(t_save), n, stream_ptr(dev))
+        if taps is not None:
+            taps.append((h_save, None))           # head: post-LeakyReLU hidden layer (its sign = active set)
         ctx.save_for_backward(x_in, *Ws, W1, W2)
         ctx.graph, ctx.kind, ctx.L = graph, kind, L
         ctx.Ys, ctx.stats, ctx.h_save, ctx.t_save = Ys, stats, h_save, t_save

@@ -49,8 +49,9 @@ class MaskedLeaky(torch.nn.Module):
 
     fp32 implementations that agree to 1e-6 still disagree on the SIGN of a pre-activation that lies within
     rounding of zero (about one element per network pass at these sizes); that element's slope flips 1 <-> 0.01 and
-    the gradients upstream of it move by ~1e-3.  Evaluating the float64 oracle on the product's own active set makes
-    the gradient comparison well-posed; the sign decisions themselves are covered by the activation parity check.
+    the gradients upstream of it move by ~1e-3.  Evaluating the fp32 oracle on the product's own active set makes the
+    gradient comparison well-posed (the forward values change by < 1e-6 at the affected elements); the sign
+    decisions themselves are covered by the activation parity check.
     """
 
     def __init__(self, masks, slope=0.01):
@@ -66,21 +67,24 @@ class MaskedLeaky(torch.nn.Module):
 
 
 def product_masks(net_d):
-    """active sets of the product's 12 trunk layers in the CALLER's node numbering (needs net_d.taps filled)."""
+    """active sets of the product's 12 trunk layers + the head's hidden layer, in the CALLER's node numbering
+    (needs net_d.taps filled)."""
     perm = torch.from_numpy(net_d.last_graph.perm_host)
     masks = []
     for y, st in net_d.taps:
-        z = (y * st[2] + st[3]).cpu()
+        z = (y * st[2] + st[3]).cpu() if st is not None else y.cpu()      # last entry: head hidden layer
         m = torch.empty_like(z, dtype=torch.bool)
         m[perm] = z > 0
         masks.append(m)
     return masks
 
 
-def oracle64_like(net_r, masks):
-    """float64 deep copy of an oracle network that uses the prescribed active sets"""
+def oracle_like(net_r, masks, double=False):
+    """deep copy of an oracle network (fp32, or float64 with double=True) that uses the prescribed active sets"""
     import copy
-    net = copy.deepcopy(net_r).double()
+    net = copy.deepcopy(net_r)
+    if double:
+        net = net.double()
     net.zero_grad()
     net.l_relu = MaskedLeaky(masks)
     return net

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from tests.helpers import (dataset64, oracle64_like, product_masks, rel_err, report, small_case)
+from tests.helpers import oracle_like, product_masks, rel_err, report, small_case
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -84,13 +84,14 @@ def test_per_layer_activations_and_grads(kind, n, reorder):
             assert e_y < 1e-4 and e_x < 1e-4, (l, e_y, e_x)
         e_out = rel_err(out_d, out_r)
         assert e_out < 1e-4
-        # ---- gradients: float64 oracle on the product's active sets (always), fp32 oracle when no sign flipped ----
+        # ---- gradients: fp32 oracle evaluated on the product's LeakyReLU active sets (well-posed even when a
+        #      pre-activation within rounding of zero got a different sign); the plain oracle too when none flipped
         flips, masks = _count_flips(net_d, taps_r)
-        net_64 = oracle64_like(net_r, masks)
-        net_64(dataset64(ds)).backward(g.double())
-        e_g64 = _compare_grads(net_d, net_64, f"{kind}{n} vs oracle64")
-        e_g32 = _compare_grads(net_d, net_r, f"{kind}{n} vs oracle32") if flips == 0 else float("nan")
-        report(f"net {type(net_d).__name__} {kind}{n} reorder={reorder}", (worst_act, e_out, e_g64, e_g32, flips))
+        net_m = oracle_like(net_r, masks)
+        net_m(ds).backward(g)
+        e_gm = _compare_grads(net_d, net_m, f"{kind}{n} vs oracle on product active sets")
+        e_g32 = _compare_grads(net_d, net_r, f"{kind}{n} vs oracle") if flips == 0 else float("nan")
+        report(f"net {type(net_d).__name__} {kind}{n} reorder={reorder}", (worst_act, e_out, e_gm, e_g32, flips))
         # BatchNorm running statistics follow the reference semantics
         for i in (1, 6, 12):
             assert rel_err(getattr(net_d, f"bn{i}").running_mean, getattr(net_r, f"bn{i}").running_mean) < 1e-4
@@ -132,13 +133,13 @@ def test_full_step_losses_and_gradients(cfg):
         e_l = max(abs(a - b.item()) / (abs(b.item()) + 1e-9) for a, b in zip(parts_d, parts_r))
         if it == 0:
             assert e_l < 1e-4, (parts_d, [p.item() for p in parts_r])
-            # gradients of the whole step: float64 oracle evaluated on the product's LeakyReLU active sets
-            p64 = oracle64_like(pr, product_masks(pd))
-            n64 = oracle64_like(nr, product_masks(nd))
-            tot64, _, _, _ = step_ref.losses(p64, n64, dataset64(ds), n_mesh, k, cfg["loop"], epoch=101)
-            tot64.backward()
-            e_gp = _compare_grads(pd, p64, "posnet step")
-            e_gn = _compare_grads(nd, n64, "normnet step")
+            # gradients of the whole step: fp32 oracle evaluated on the product's LeakyReLU active sets
+            pm, nm = oracle_like(pr, product_masks(pd)), oracle_like(nr, product_masks(nd))
+            pm.train(); nm.train()
+            totm, _, _, _ = step_ref.losses(pm, nm, ds, n_mesh, k, cfg["loop"], epoch=101)
+            totm.backward()
+            e_gp = _compare_grads(pd, pm, "posnet step")
+            e_gn = _compare_grads(nd, nm, "normnet step")
             report(f"step k={k} loop={cfg['loop']}", (e_l, e_gp, e_gn))
         else:
             # Adam turns rounding noise of near-zero gradients into +-lr steps (sign-like update), so later

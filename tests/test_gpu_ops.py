@@ -269,7 +269,7 @@ TC_SHAPES = [(64, 64), (64, 128), (128, 256), (256, 512), (512, 512), (512, 256)
 
 
 @pytest.mark.parametrize("cin,cout", TC_SHAPES)
-@pytest.mark.parametrize("n", [640, 1000, 4099])
+@pytest.mark.parametrize("n", [640, 1000, 4099, 20011])
 def test_gemm_tcgen05_3xtf32(cin, cout, n):
     """tcgen05 kind::tf32 path with the hi/lo split: fp32-level accuracy against a float64 evaluation"""
     from dual_dmp_b200 import functional as F_
@@ -287,10 +287,15 @@ def test_gemm_tcgen05_3xtf32(cin, cout, n):
     e2 = rel_err(F_.gemm_xw(Xn, Wd, scale=sc, shift=sh, backend=2), act[:n] @ W.double().t())
     e3 = rel_err(F_.gemm_xw(Xd, Wd, row_map=rm, n=n, backend=2), X[rmap.long()].double() @ W.double().t())
     e4 = rel_err(F_.gemm_dx(dHd, Wd, backend=2), dH.double() @ W.double())
-    report(f"gemm_tc cin={cin} cout={cout} n={n}", (e1, e2, e3, e4))
-    assert max(e1, e2, e3, e4) < 5e-6, (e1, e2, e3, e4)
+    e5 = rel_err(F_.gemm_dw(dHd, Xn, cin, backend=2), dH.double().t() @ X[:n].double())
+    e6 = rel_err(F_.gemm_dw(dHd, Xn, cin, scale=sc, shift=sh, backend=2), dH.double().t() @ act[:n])
+    report(f"gemm_tc cin={cin} cout={cout} n={n}", (e1, e2, e3, e4, e5, e6))
+    assert max(e1, e2, e3, e4) < 1e-5, (e1, e2, e3, e4)
+    assert max(e5, e6) < 2e-5, (e5, e6)
+    assert torch.equal(F_.gemm_dw(dHd, Xn, cin, scale=sc, shift=sh, backend=2),
+                       F_.gemm_dw(dHd, Xn, cin, scale=sc, shift=sh, backend=2))
     a = F_.gemm_xw(Xn, Wd, scale=sc, shift=sh, backend=2)
     b = F_.gemm_xw(Xn, Wd, scale=sc, shift=sh, backend=2)
     assert torch.equal(a, b)
     # and it agrees with the FFMA kernel to fp32 rounding
-    assert rel_err(a, F_.gemm_xw(Xn, Wd, scale=sc, shift=sh, backend=1)) < 5e-6
+    assert rel_err(a, F_.gemm_xw(Xn, Wd, scale=sc, shift=sh, backend=1)) < 1e-5
