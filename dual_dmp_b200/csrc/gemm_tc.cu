@@ -95,14 +95,15 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
 
 // ---- descriptors ----------------------------------------------------------------------------------------------------
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) |
-// version=1 [46,48) | layout_type [61,64) (2 = SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// version=1 [46,48) | layout_type [61,64) (2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint32_t layout_type = 2) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr >> 4) & 0x3FFF);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
+    d |= (uint64_t)layout_type << 61;
     return d;
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor) for kind::tf32, fp32 accumulate
@@ -315,8 +316,9 @@ static int run_nt(const float* A, const int* a_map, const float* scale, const fl
 // Work item = (row segment of kSegRows rows, output tile); items are dealt round-robin to persistent CTAs with the
 // tile index fastest, so CTAs running together read the same rows (L2 reuse).  Every item writes its own partial
 // tile; a fixed-order float64 reduction sums the segments (deterministic, and it bounds the fp32 accumulation
-// length inside TMEM to kSegRows).
-constexpr int kSegRows = 8192;
+// length inside TMEM to kSegRows: the tensor core truncates when it accumulates, so the error grows linearly
+// with the chain length, measured ~7e-9 per row).
+constexpr int kSegRows = 2048;
 
 struct TnArgs {
     const float* A;       // dH [rows, M] row-major
@@ -337,7 +339,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_tn_kernel(const TnArgs g)
     constexpr uint32_t B_BYTES = BN * 128;
     constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
     constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
-    constexpr uint32_t LBO = (BK / 8) * 1024;        // next 32-wide MN block (layout [mn_blk][k_grp][8][128B])
+    constexpr uint32_t LBO = (BK / 4) * 512;         // next 32-wide MN block (layout [mn_blk][k4_grp][4][128B])
+    constexpr uint32_t SBO = 512;                    // next group of 4 k-rows
     constexpr int A_CH = BM / 4, B_CH = BN / 4;      // 16-byte chunks per k-row
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -408,7 +411,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_tn_kernel(const TnArgs g)
                     uint4 hi, lo;
                     split_tf32(av[j].x, hi.x, lo.x); split_tf32(av[j].y, hi.y, lo.y);
                     split_tf32(av[j].z, hi.z, lo.z); split_tf32(av[j].w, hi.w, lo.w);
-                    const uint32_t off = a_off0 + (k >> 3) * 1024u + (k & 7u) * 128u + (((a_cm & 7u) ^ (k & 7u)) << 4);
+                    const uint32_t off = a_off0 + (k >> 2) * SBO + (k & 3u) * 128u + ((((a_cm & 7u) >> 1) ^ (k & 3u)) << 5) +
+                                         ((a_cm & 1u) << 4);
                     *reinterpret_cast<uint4*>(st + off) = hi;
                     *reinterpret_cast<uint4*>(st + A_BYTES + off) = lo;
                 }
@@ -423,7 +427,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_tn_kernel(const TnArgs g)
                     uint4 hi, lo;
                     split_tf32(b.x, hi.x, lo.x); split_tf32(b.y, hi.y, lo.y);
                     split_tf32(b.z, hi.z, lo.z); split_tf32(b.w, hi.w, lo.w);
-                    const uint32_t off = b_off0 + (k >> 3) * 1024u + (k & 7u) * 128u + (((b_cm & 7u) ^ (k & 7u)) << 4);
+                    const uint32_t off = b_off0 + (k >> 2) * SBO + (k & 3u) * 128u + ((((b_cm & 7u) >> 1) ^ (k & 3u)) << 5) +
+                                         ((b_cm & 1u) << 4);
                     *reinterpret_cast<uint4*>(st + 2 * A_BYTES + off) = hi;
                     *reinterpret_cast<uint4*>(st + 2 * A_BYTES + B_BYTES + off) = lo;
                 }
@@ -466,11 +471,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_tn_kernel(const TnArgs g)
                     const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
 #pragma unroll
                     for (int ks = 0; ks < BK / UMMA_K; ++ks) {
-                        const uint32_t koff = ks * 1024u;                       // next group of 8 k-rows
-                        const uint64_t a_hi = make_desc(sa + koff, LBO, 1024);
-                        const uint64_t a_lo = make_desc(sa + A_BYTES + koff, LBO, 1024);
-                        const uint64_t b_hi = make_desc(sa + 2 * A_BYTES + koff, LBO, 1024);
-                        const uint64_t b_lo = make_desc(sa + 2 * A_BYTES + B_BYTES + koff, LBO, 1024);
+                        const uint32_t koff = ks * 2u * SBO;                    // 8 k-rows = two 4-row groups
+                        const uint64_t a_hi = make_desc(sa + koff, LBO, SBO, 1);
+                        const uint64_t a_lo = make_desc(sa + A_BYTES + koff, LBO, SBO, 1);
+                        const uint64_t b_hi = make_desc(sa + 2 * A_BYTES + koff, LBO, SBO, 1);
+                        const uint64_t b_lo = make_desc(sa + 2 * A_BYTES + B_BYTES + koff, LBO, SBO, 1);
                         umma_tf32(tmem_base, a_lo, b_hi, idesc, (kb | ks) != 0);
                         umma_tf32(tmem_base, a_hi, b_lo, idesc, 1);
                         umma_tf32(tmem_base, a_hi, b_hi, idesc, 1);
