@@ -72,3 +72,14 @@ def test_state_dict_layout_matches_oracle():
         assert list(sa.keys()) == list(sb.keys())
         assert all(sa[k].shape == sb[k].shape for k in sa)
         a.load_state_dict(sb)
+
+
+def test_util_shim():
+    """`import util.networks` etc. resolve to the drop-in when dual_dmp_b200/dropin is on the path"""
+    import sys
+    code = ("import util.loss as Loss, util.models as Models, util.datamaker as Datamaker\n"
+            "from util.mesh import Mesh\nfrom util.networks import PosNet, NormalNet\n"
+            "import dual_dmp_b200.util.networks as N\nassert PosNet is N.PosNet and NormalNet is N.NormalNet\n"
+            "assert Loss.fn_bnf_loss and Models.vertex_updating and Datamaker.create_dataset and Mesh\n")
+    env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.path.join(ROOT, "dual_dmp_b200", "dropin"))
+    subprocess.run([sys.executable, "-c", code], check=True, env=env, cwd="/tmp")

@@ -1,0 +1,101 @@
+"""Size-independent properties at the benchmark size (1M faces), where the oracle cannot run: determinism,
+permutation equivariance of the Morton reorder, the A_hat symmetry checksum of the SpMM, tcgen05 vs FFMA GEMM."""
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import rel_err, report
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def big():
+    from dual_dmp_b200 import synth
+    from dual_dmp_b200.util.datamaker import dataset_from_meshes
+    from dual_dmp_b200.util.mesh import Mesh
+    case = synth.make_case(224)
+    n_mesh, s_mesh = Mesh(vs=case.noise_vs, faces=case.faces), Mesh(vs=case.smooth_vs, faces=case.faces)
+    return n_mesh, s_mesh, dataset_from_meshes(n_mesh, s_mesh)
+
+
+def test_graph_build_invariants_1m(big):
+    from dual_dmp_b200.graph import GcnGraph
+    n_mesh, _, ds = big
+    F, V = len(n_mesh.faces), len(n_mesh.vs)
+    assert (F, V) == (1003520, 501762) and len(n_mesh.edges) == 1505280
+    deg = n_mesh.v_dims.numpy()
+    assert (deg == 5).sum() == 12 and (deg == 6).sum() == V - 12 and (n_mesh.f2f >= 0).all()
+    g = GcnGraph(ds.face_index, F, DEV, coords=ds.z2.detach()[:, :3])
+    assert g.symmetric and g.nnz == 4 * F and not g.identity
+    rowptr = g.rowptr.cpu().numpy()
+    assert (np.diff(rowptr) == 4).all()
+    assert torch.allclose(g.w, torch.full_like(g.w, 0.25))
+    # locality of the Morton order: median |row - col| is tiny compared with F
+    col = g.col.cpu().numpy().astype(np.int64)
+    rows = np.repeat(np.arange(F), 4)
+    assert np.median(np.abs(rows - col)) < 2000
+
+
+def test_spmm_checksum_and_determinism_1m(big):
+    """A_hat symmetric  =>  1^T (A_hat H) = (A_hat 1)^T H ;  two runs are bitwise identical"""
+    from dual_dmp_b200 import functional as F_
+    from dual_dmp_b200.graph import GcnGraph
+    n_mesh, _, ds = big
+    V = len(n_mesh.vs)
+    g = GcnGraph(ds.edge_index, V, DEV, coords=ds.x_pos)
+    torch.manual_seed(0)
+    for C in (64, 512):
+        H = torch.randn(V, C, device=DEV)
+        Y, partials = F_.spmm_gcn(g, H, stats=True)
+        Y2, partials2 = F_.spmm_gcn(g, H, stats=True)
+        assert torch.equal(Y, Y2) and torch.equal(partials, partials2)
+        rowsum = F_.spmm_gcn(g, torch.ones(V, 4, device=DEV))[:, 0].double()
+        lhs = Y.double().sum(dim=0)
+        rhs = (rowsum[:, None] * H.double()).sum(dim=0)
+        e = rel_err(lhs, rhs)
+        report(f"spmm checksum 1M C={C}", e)
+        assert e < 1e-5
+        assert rel_err(partials.double().sum(dim=0)[0], lhs) < 1e-6
+
+
+def test_tc_and_ffma_gemm_agree_1m():
+    from dual_dmp_b200 import functional as F_
+    torch.manual_seed(1)
+    n = 300001
+    X = torch.randn(n, 256, device=DEV)
+    W = torch.randn(512, 256, device=DEV) / 16
+    dH = torch.randn(n, 512, device=DEV)
+    sc, sh = torch.rand(256, device=DEV) + 0.5, torch.randn(256, device=DEV)
+    assert rel_err(F_.gemm_xw(X, W, scale=sc, shift=sh, backend=2), F_.gemm_xw(X, W, scale=sc, shift=sh, backend=1)) < 1e-5
+    assert rel_err(F_.gemm_dx(dH, W, backend=2), F_.gemm_dx(dH, W, backend=1)) < 1e-5
+    a, b = F_.gemm_dw(dH, X, 256, scale=sc, shift=sh, backend=2), F_.gemm_dw(dH, X, 256, scale=sc, shift=sh, backend=1)
+    e = rel_err(a, b)
+    report("gemm_dw tc vs ffma n=300001", e)
+    assert e < 5e-5
+
+
+def test_network_equivariance_and_determinism_1m(big):
+    """the Morton relabelling must not change the result (this is what legitimises the reorder); reruns are bitwise
+    identical; outputs are finite and NormalNet rows are unit vectors"""
+    from dual_dmp_b200.util.networks import NormalNet, PosNet
+    n_mesh, _, ds = big
+    torch.manual_seed(0)
+    for cls in (PosNet, NormalNet):
+        net = cls(DEV).to(DEV)
+        net.train()
+        with torch.no_grad():
+            pass
+        a = net(ds).detach().clone()
+        b = net(ds).detach().clone()
+        assert torch.equal(a, b) and torch.isfinite(a).all()
+        net.reorder = False
+        c = net(ds).detach()
+        e = rel_err(a, c)
+        report(f"equivariance 1M {cls.__name__}", e)
+        assert e < 1e-4
+        if cls is NormalNet:
+            assert (a.norm(dim=1) - 1).abs().max() < 1e-5
+        del net, a, b, c
+        torch.cuda.empty_cache()
