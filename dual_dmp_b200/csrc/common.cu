@@ -59,10 +59,9 @@ int ddmp_device_info(int* sm_count, int* cc_major, int* cc_minor) {
 
 int ddmp_rows_per_block(int32_t C) {
     if (C <= 0) return 0;
-    int r = 65536 / C;
-    if (r < 128) r = 128;
-    if (r > 1024) r = 1024;
-    return r;
+    // 128 rows per CTA for the wide layers, 256 for the narrow ones: >= 3,900 CTAs at 1M rows (a grid of 980 CTAs,
+    // as with 1024 rows per block, leaves a mostly empty second wave: ncu, profiles/)
+    return C <= 64 ? 256 : 128;
 }
 
 int64_t ddmp_num_row_blocks(int64_t n, int32_t C) {

@@ -13,10 +13,10 @@ int ffma_gemm_dw(const float*, const float*, const int32_t*, const float*, const
 bool tc_supported_xw(int64_t n, int32_t Cin, int32_t Cout);
 bool tc_supported_dx(int64_t n, int32_t Cin, int32_t Cout);
 bool tc_supported_dw(int64_t n, int32_t Cin, int32_t Cout);
-int tc_gemm_xw(const float*, const int32_t*, const float*, const float*, float, const float*, float*, int64_t,
-               int32_t, int32_t, cudaStream_t);
-int tc_gemm_dx(const float*, const float*, float*, int64_t, int32_t, int32_t, cudaStream_t);
-int transpose(const float*, float*, int32_t, int32_t, cudaStream_t);
+int64_t tc_gemm_nt_workspace_bytes(int32_t, int32_t);
+int tc_gemm_xw(const float*, const int32_t*, const float*, const float*, float, const float*, float*, void*, int64_t,
+               int64_t, int32_t, int32_t, cudaStream_t);
+int tc_gemm_dx(const float*, const float*, float*, void*, int64_t, int64_t, int32_t, int32_t, cudaStream_t);
 int64_t tc_gemm_dw_workspace_bytes(int64_t, int32_t, int32_t);
 int tc_gemm_dw(const float*, const float*, const int32_t*, const float*, const float*, float, float*, void*,
                int64_t, int64_t, int32_t, int32_t, cudaStream_t);
@@ -24,9 +24,10 @@ int tc_gemm_dw(const float*, const float*, const int32_t*, const float*, const f
 static bool tc_supported_xw(int64_t, int32_t, int32_t) { return false; }
 static bool tc_supported_dx(int64_t, int32_t, int32_t) { return false; }
 static bool tc_supported_dw(int64_t, int32_t, int32_t) { return false; }
-static int tc_gemm_xw(const float*, const int32_t*, const float*, const float*, float, const float*, float*, int64_t,
-                      int32_t, int32_t, cudaStream_t) { return DDMP_ERR_UNSUPPORTED; }
-static int tc_gemm_dx(const float*, const float*, float*, int64_t, int32_t, int32_t, cudaStream_t) {
+static int64_t tc_gemm_nt_workspace_bytes(int32_t, int32_t) { return 0; }
+static int tc_gemm_xw(const float*, const int32_t*, const float*, const float*, float, const float*, float*, void*,
+                      int64_t, int64_t, int32_t, int32_t, cudaStream_t) { return DDMP_ERR_UNSUPPORTED; }
+static int tc_gemm_dx(const float*, const float*, float*, void*, int64_t, int64_t, int32_t, int32_t, cudaStream_t) {
     return DDMP_ERR_UNSUPPORTED;
 }
 static int64_t tc_gemm_dw_workspace_bytes(int64_t, int32_t, int32_t) { return 0; }
@@ -37,47 +38,44 @@ static int tc_gemm_dw(const float*, const float*, const int32_t*, const float*, 
 
 extern "C" {
 
+int64_t ddmp_gemm_workspace_bytes(int64_t n, int32_t Cin, int32_t Cout) {
+    using namespace ddmp;
+    if (n <= 0 || Cin <= 0 || Cout <= 0) return 0;
+    return (tc_supported_xw(n, Cin, Cout) || tc_supported_dx(n, Cin, Cout)) ? tc_gemm_nt_workspace_bytes(Cin, Cout) : 0;
+}
+
 int ddmp_gemm_xw(const float* X, const int32_t* row_map, const float* scale, const float* shift, float slope,
-                 const float* W, float* H, int64_t n, int32_t Cin, int32_t Cout, int backend, void* stream) {
+                 const float* W, float* H, void* workspace, int64_t workspace_bytes, int64_t n, int32_t Cin,
+                 int32_t Cout, int backend, void* stream) {
     using namespace ddmp;
     DDMP_REQUIRE(X && W && H, "gemm_xw: null pointer");
     DDMP_REQUIRE((scale == nullptr) == (shift == nullptr), "gemm_xw: scale and shift must come together");
     DDMP_REQUIRE(n >= 0 && Cin > 0 && Cout > 0, "gemm_xw: bad shape");
     if (n == 0) return DDMP_OK;
-    const bool tc_ok = tc_supported_xw(n, Cin, Cout);
+    const bool tc_ok = tc_supported_xw(n, Cin, Cout) && workspace != nullptr;
     if (backend == DDMP_GEMM_TC && !tc_ok) {
         set_error("gemm_xw: tcgen05 path does not support n=%lld Cin=%d Cout=%d", (long long)n, Cin, Cout);
         return DDMP_ERR_UNSUPPORTED;
     }
     if (backend == DDMP_GEMM_TC || (backend == DDMP_GEMM_AUTO && tc_ok))
-        return tc_gemm_xw(X, row_map, scale, shift, slope, W, H, n, Cin, Cout, as_stream(stream));
+        return tc_gemm_xw(X, row_map, scale, shift, slope, W, H, workspace, workspace_bytes, n, Cin, Cout,
+                          as_stream(stream));
     return ffma_gemm_xw(X, row_map, scale, shift, slope, W, H, n, Cin, Cout, as_stream(stream));
 }
 
-int ddmp_transpose(const float* src, float* dst, int32_t rows, int32_t cols, void* stream) {
-    using namespace ddmp;
-    DDMP_REQUIRE(src && dst && rows > 0 && cols > 0 && src != dst, "transpose: bad arguments");
-#ifdef DDMP_WITH_TC
-    return transpose(src, dst, rows, cols, as_stream(stream));
-#else
-    set_error("transpose: built without the tcgen05 path");
-    return DDMP_ERR_UNSUPPORTED;
-#endif
-}
-
-int ddmp_gemm_dx(const float* dH, const float* W, const float* Wt, float* gX, int64_t n, int32_t Cin, int32_t Cout,
-                 int backend, void* stream) {
+int ddmp_gemm_dx(const float* dH, const float* W, float* gX, void* workspace, int64_t workspace_bytes, int64_t n,
+                 int32_t Cin, int32_t Cout, int backend, void* stream) {
     using namespace ddmp;
     DDMP_REQUIRE(dH && W && gX, "gemm_dx: null pointer");
     DDMP_REQUIRE(n >= 0 && Cin > 0 && Cout > 0, "gemm_dx: bad shape");
     if (n == 0) return DDMP_OK;
-    const bool tc_ok = tc_supported_dx(n, Cin, Cout) && Wt != nullptr;
+    const bool tc_ok = tc_supported_dx(n, Cin, Cout) && workspace != nullptr;
     if (backend == DDMP_GEMM_TC && !tc_ok) {
         set_error("gemm_dx: tcgen05 path does not support n=%lld Cin=%d Cout=%d", (long long)n, Cin, Cout);
         return DDMP_ERR_UNSUPPORTED;
     }
     if (backend == DDMP_GEMM_TC || (backend == DDMP_GEMM_AUTO && tc_ok))
-        return tc_gemm_dx(dH, Wt, gX, n, Cin, Cout, as_stream(stream));
+        return tc_gemm_dx(dH, W, gX, workspace, workspace_bytes, n, Cin, Cout, as_stream(stream));
     return ffma_gemm_dx(dH, W, gX, n, Cin, Cout, as_stream(stream));
 }
 

@@ -10,6 +10,8 @@
 // into the 128-byte-swizzled UMMA canonical layout, one elected thread of a 9th warp issues the MMAs, and all
 // producer warps drain the TMEM accumulator in the epilogue.  Pipeline: `full`/`empty` mbarriers per smem stage,
 // tcgen05.commit releases a stage / publishes the accumulator.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace ddmp {
@@ -86,12 +88,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// tf32 split: hi = rna(x), lo = rna(x - hi)
+// tf32 split x = hi + lo: hi = x rounded to 10 mantissa bits (round-half-up in magnitude with an integer add, 2
+// ops instead of the ~5 that cvt.rna.tf32 expands to), lo = exact remainder x - hi with its low 13 bits cleared
+// (|lo| <= 2^-11 |x|, so the dropped part is <= 2^-22 |x|).
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
-    const float r = x - __uint_as_float(hi);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+    hi = (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u;
+    lo = __float_as_uint(x - __uint_as_float(hi)) & 0xFFFFE000u;
 }
+__device__ __forceinline__ void sts128(uint32_t saddr, const uint4& v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ float lrelu_max(float z, float slope) { return fmaxf(z, z * slope); }   // 0 < slope < 1
 
 // ---- descriptors ----------------------------------------------------------------------------------------------------
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) |
@@ -164,6 +172,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_nt_kernel(const NtArgs g)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const uint32_t smem_base = smem_u32(smem);
 
     if (warp < kProducerWarps) {
         // ===== producers: global -> (act, split) -> swizzled smem =====
@@ -197,21 +206,21 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_nt_kernel(const NtArgs g)
             if (has_act) { sc = ldg4(g.scale + k0); sh = ldg4(g.shift + k0); }
 
             mbar_wait(empty_bar + s, ph ^ 1u);
-            uint8_t* st = smem + s * STAGE_BYTES;
+            const uint32_t st = smem_base + s * STAGE_BYTES;
 #pragma unroll
             for (int j = 0; j < BM * 8 / kProducerThreads; ++j) {
                 const uint32_t row = (t >> 3) + j * (kProducerThreads / 8);
                 float4 a = av[j];
                 if (has_act && (m0 + row) < g.M) {
-                    a.x = lrelu(fmaf(a.x, sc.x, sh.x), g.slope); a.y = lrelu(fmaf(a.y, sc.y, sh.y), g.slope);
-                    a.z = lrelu(fmaf(a.z, sc.z, sh.z), g.slope); a.w = lrelu(fmaf(a.w, sc.w, sh.w), g.slope);
+                    a.x = lrelu_max(fmaf(a.x, sc.x, sh.x), g.slope); a.y = lrelu_max(fmaf(a.y, sc.y, sh.y), g.slope);
+                    a.z = lrelu_max(fmaf(a.z, sc.z, sh.z), g.slope); a.w = lrelu_max(fmaf(a.w, sc.w, sh.w), g.slope);
                 }
                 uint4 hi, lo;
                 split_tf32(a.x, hi.x, lo.x); split_tf32(a.y, hi.y, lo.y);
                 split_tf32(a.z, hi.z, lo.z); split_tf32(a.w, hi.w, lo.w);
                 const uint32_t off = sw128(row, c);
-                *reinterpret_cast<uint4*>(st + off) = hi;
-                *reinterpret_cast<uint4*>(st + A_BYTES + off) = lo;
+                sts128(st + off, hi);
+                sts128(st + A_BYTES + off, lo);
             }
 #pragma unroll
             for (int j = 0; j < BN * 8 / kProducerThreads; ++j) {
@@ -221,8 +230,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_nt_kernel(const NtArgs g)
                 split_tf32(b.x, hi.x, lo.x); split_tf32(b.y, hi.y, lo.y);
                 split_tf32(b.z, hi.z, lo.z); split_tf32(b.w, hi.w, lo.w);
                 const uint32_t off = sw128(row, c);
-                *reinterpret_cast<uint4*>(st + 2 * A_BYTES + off) = hi;
-                *reinterpret_cast<uint4*>(st + 2 * A_BYTES + B_BYTES + off) = lo;
+                sts128(st + 2 * A_BYTES + off, hi);
+                sts128(st + 2 * A_BYTES + B_BYTES + off, lo);
             }
             fence_proxy_async();                 // make the generic-proxy stores visible to the tensor-core proxy
             __syncwarp();
@@ -308,6 +317,261 @@ static int run_nt(const float* A, const int* a_map, const float* scale, const fl
     return launch_nt<64, 4>(g, st);
 }
 
+// ---- NT kernel, version 2: persistent, B streamed by TMA bulk copies, epilogue overlapped ---------------------------
+// The weights (B operand) are split into hi/lo and laid out ONCE per call in the exact swizzled shared-memory image
+// (tc_prep_b_kernel: [n_tile][k_block][hi|lo][BN rows x 128 B]), so a stage's B part is one contiguous blob that a
+// single thread streams with cp.async.bulk (SASS UBLKCP) onto the stage's `full` mbarrier.  Only the activation
+// operand still goes through the producer warps (BatchNorm + LeakyReLU + split need registers).  CTAs are persistent
+// (tile = blockIdx.x + i*gridDim.x, n-tile fastest so the CTAs that share an A row block run together), the
+// accumulator is double-buffered in TMEM (2 x BN columns) and four dedicated warps drain tile i while tile i+1 is
+// being multiplied.
+constexpr int kV2Threads = 16 * 32;   // warps 0-7 producers | 8 MMA | 9 B loader | 10,11 idle | 12-15 epilogue
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+struct Nt2Args {
+    const float* A;
+    const uint8_t* Bimg;  // pre-split, pre-swizzled weights
+    float* C;
+    const int* a_map;
+    const float* scale;
+    const float* shift;
+    float slope;
+    int64_t M;
+    int N, K;
+    int tiles_n;
+    int64_t num_tiles;
+};
+
+// W [N,K] (or, transposed, W^T given as [K,N]) -> image; one thread per (n, 16-byte chunk of K)
+__global__ void tc_prep_b_kernel(const float* __restrict__ W, int transposed, uint8_t* __restrict__ img, int N, int K,
+                                 int BN) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int kc = K / 4;
+    if (i >= (int64_t)N * kc) return;
+    const int n = (int)(i / kc), k = (int)(i % kc) * 4;
+    float4 v;
+    if (!transposed) {
+        v = ldg4(W + (int64_t)n * K + k);
+    } else {
+        v.x = __ldg(W + (int64_t)(k + 0) * N + n); v.y = __ldg(W + (int64_t)(k + 1) * N + n);
+        v.z = __ldg(W + (int64_t)(k + 2) * N + n); v.w = __ldg(W + (int64_t)(k + 3) * N + n);
+    }
+    uint4 hi, lo;
+    split_tf32(v.x, hi.x, lo.x); split_tf32(v.y, hi.y, lo.y); split_tf32(v.z, hi.z, lo.z); split_tf32(v.w, hi.w, lo.w);
+    const int n_tile = n / BN, r = n % BN, kb = k / BK, c = (k % BK) / 4;
+    const int num_kb = K / BK;
+    const int64_t base = ((int64_t)n_tile * num_kb + kb) * 2 * ((int64_t)BN * 128);
+    const uint32_t off = sw128((uint32_t)r, (uint32_t)c);
+    *reinterpret_cast<uint4*>(img + base + off) = hi;
+    *reinterpret_cast<uint4*>(img + base + (int64_t)BN * 128 + off) = lo;
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kV2Threads, 1) tc_gemm_nt2_kernel(const Nt2Args g) {
+    constexpr uint32_t A_BYTES = BM * 128;
+    constexpr uint32_t B_BYTES = BN * 128;
+    constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    constexpr uint32_t TMEM_COLS = 2 * BN;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* acc_full = empty_bar + STAGES;     // [2]
+    uint64_t* acc_empty = acc_full + 2;          // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_kb = g.K / BK;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar + s, kProducerWarps + 1);
+            mbar_init(empty_bar + s, 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(acc_full + b, 1);
+            mbar_init(acc_empty + b, 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 8) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t smem_base = smem_u32(smem);
+
+    if (warp < kProducerWarps) {
+        // ===== A producers =====
+        const int t = threadIdx.x;
+        const uint32_t c = t & 7;
+        const bool has_act = g.scale != nullptr;
+        uint32_t it = 0;
+        for (int64_t tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+            const int64_t m0 = (tile / g.tiles_n) * BM;
+            int64_t src_row[BM * 8 / kProducerThreads];
+#pragma unroll
+            for (int j = 0; j < BM * 8 / kProducerThreads; ++j) {
+                const int64_t m = m0 + (t >> 3) + j * (kProducerThreads / 8);
+                src_row[j] = (m < g.M) ? (g.a_map ? (int64_t)__ldg(g.a_map + m) : m) : -1;
+            }
+            for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                const int k0 = kb * BK + c * 4;
+                float4 av[BM * 8 / kProducerThreads];
+#pragma unroll
+                for (int j = 0; j < BM * 8 / kProducerThreads; ++j)
+                    av[j] = (src_row[j] >= 0) ? ldg4(g.A + src_row[j] * g.K + k0) : make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (has_act) { sc = ldg4(g.scale + k0); sh = ldg4(g.shift + k0); }
+                mbar_wait(empty_bar + s, ph ^ 1u);
+                const uint32_t st = smem_base + s * STAGE_BYTES;
+#pragma unroll
+                for (int j = 0; j < BM * 8 / kProducerThreads; ++j) {
+                    const uint32_t row = (t >> 3) + j * (kProducerThreads / 8);
+                    float4 a = av[j];
+                    if (has_act && src_row[j] >= 0) {
+                        a.x = lrelu_max(fmaf(a.x, sc.x, sh.x), g.slope); a.y = lrelu_max(fmaf(a.y, sc.y, sh.y), g.slope);
+                        a.z = lrelu_max(fmaf(a.z, sc.z, sh.z), g.slope); a.w = lrelu_max(fmaf(a.w, sc.w, sh.w), g.slope);
+                    }
+                    uint4 hi, lo;
+                    split_tf32(a.x, hi.x, lo.x); split_tf32(a.y, hi.y, lo.y);
+                    split_tf32(a.z, hi.z, lo.z); split_tf32(a.w, hi.w, lo.w);
+                    const uint32_t off = sw128(row, c);
+                    sts128(st + off, hi);
+                    sts128(st + A_BYTES + off, lo);
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full_bar + s);
+            }
+        }
+    } else if (warp == 8) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BM, BN, false, false);
+            uint32_t it = 0, tile_no = 0;
+            for (int64_t tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++tile_no) {
+                const uint32_t buf = tile_no & 1u;
+                mbar_wait(acc_empty + buf, ((tile_no >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * BN;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(full_bar + s, ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + s * STAGE_BYTES;
+#pragma unroll
+                    for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+                        const uint32_t koff = ks * UMMA_K * 4;
+                        const uint64_t a_hi = make_desc(sa + koff, 16, 1024);
+                        const uint64_t a_lo = make_desc(sa + A_BYTES + koff, 16, 1024);
+                        const uint64_t b_hi = make_desc(sa + 2 * A_BYTES + koff, 16, 1024);
+                        const uint64_t b_lo = make_desc(sa + 2 * A_BYTES + B_BYTES + koff, 16, 1024);
+                        umma_tf32(d_tmem, a_lo, b_hi, idesc, (kb | ks) != 0);
+                        umma_tf32(d_tmem, a_hi, b_lo, idesc, 1);
+                        umma_tf32(d_tmem, a_hi, b_hi, idesc, 1);
+                    }
+                    umma_commit(empty_bar + s);
+                }
+                umma_commit(acc_full + buf);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 9) {
+        // ===== B loader: one bulk copy per stage =====
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int64_t tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+                const int tn = (int)(tile % g.tiles_n);
+                const uint8_t* src = g.Bimg + (int64_t)tn * num_kb * (2 * (int64_t)B_BYTES);
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(empty_bar + s, ph ^ 1u);
+                    mbar_arrive_expect_tx(full_bar + s, 2 * B_BYTES);
+                    bulk_g2s(smem_base + s * STAGE_BYTES + 2 * A_BYTES, src + (int64_t)kb * (2 * (int64_t)B_BYTES),
+                             2 * B_BYTES, full_bar + s);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 12) {
+        // ===== epilogue: TMEM -> registers -> global, overlapped with the next tile's main loop =====
+        const int q = warp & 3;
+        uint32_t tile_no = 0;
+        for (int64_t tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++tile_no) {
+            const uint32_t buf = tile_no & 1u;
+            const int64_t m = (tile / g.tiles_n) * BM + q * 32 + lane;
+            const int n0 = (int)(tile % g.tiles_n) * BN;
+            mbar_wait(acc_full + buf, (tile_no >> 1) & 1u);
+            tc_fence_after();
+#pragma unroll 1
+            for (int cb = 0; cb < BN; cb += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)cb, v);
+                if (m < g.M) {
+                    float* dst = g.C + m * g.N + n0 + cb;
+#pragma unroll
+                    for (int e = 0; e < 32; e += 4)
+                        st4(dst + e, make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]),
+                                                 __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3])));
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty + buf);
+        }
+    }
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+template <int BN, int STAGES>
+static int launch_nt2(const Nt2Args& g, cudaStream_t st) {
+    constexpr size_t smem = (size_t)STAGES * (2 * BM * 128 + 2 * BN * 128) + 1024 + 256;
+    static bool configured = false;
+    if (!configured) {
+        DDMP_CUDA(cudaFuncSetAttribute(tc_gemm_nt2_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+        configured = true;
+    }
+    const int64_t grid = g.num_tiles < kNumSMs ? g.num_tiles : kNumSMs;
+    tc_gemm_nt2_kernel<BN, STAGES><<<(unsigned)grid, kV2Threads, smem, st>>>(g);
+    return check_launch("tc_gemm_nt2");
+}
+
+// B = W [N,K] row-major (transposed == 0) or B = W^T where W is [K,N] row-major (transposed == 1)
+static int run_nt2(const float* A, const int* a_map, const float* scale, const float* shift, float slope,
+                   const float* W, int transposed, void* workspace, float* C, int64_t M, int N, int K,
+                   cudaStream_t st) {
+    const int BN = (N % 256 == 0) ? 256 : ((N % 128 == 0) ? 128 : 64);
+    uint8_t* img = reinterpret_cast<uint8_t*>(workspace);
+    const int64_t chunks = (int64_t)N * (K / 4);
+    tc_prep_b_kernel<<<(unsigned)ceil_div(chunks, 256), 256, 0, st>>>(W, transposed, img, N, K, BN);
+    int rc = check_launch("tc_prep_b");
+    if (rc) return rc;
+    Nt2Args g{};
+    g.A = A; g.Bimg = img; g.C = C; g.a_map = a_map; g.scale = scale; g.shift = shift; g.slope = slope;
+    g.M = M; g.N = N; g.K = K; g.tiles_n = N / BN;
+    g.num_tiles = ceil_div(M, BM) * g.tiles_n;
+    if (BN == 256) return launch_nt2<256, 2>(g, st);
+    if (BN == 128) return launch_nt2<128, 3>(g, st);
+    return launch_nt2<64, 4>(g, st);
+}
+
 // ---- TN kernel (dW) -------------------------------------------------------------------------------------------------
 // dW[M=Cout, N=Cin] = sum over rows r of A[r, m] * act(B)[r, n].  Both operands are MN-major: a K index is a graph
 // row, and a row of dH / X is contiguous along the channel.  SWIZZLE_128B MN-major canonical layout (CUTLASS
@@ -365,6 +629,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_tn_kernel(const TnArgs g)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const uint32_t smem_base = smem_u32(smem);
     const int tiles = g.tiles_m * g.tiles_n;
 
     uint32_t it = 0;                                 // pipeline iteration counter, runs across items
@@ -404,7 +669,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_tn_kernel(const TnArgs g)
                     bv[j] = (r < r1) ? ldg4(g.B + r * g.N + n0 + b_cm * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
                 mbar_wait(empty_bar + s, ph ^ 1u);
-                uint8_t* st = smem + s * STAGE_BYTES;
+                const uint32_t st = smem_base + s * STAGE_BYTES;
 #pragma unroll
                 for (int j = 0; j < BK / A_PASS; ++j) {
                     const uint32_t k = a_r + j * A_PASS;                        // k-row inside the stage
@@ -413,24 +678,24 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_tn_kernel(const TnArgs g)
                     split_tf32(av[j].z, hi.z, lo.z); split_tf32(av[j].w, hi.w, lo.w);
                     const uint32_t off = a_off0 + (k >> 2) * SBO + (k & 3u) * 128u + ((((a_cm & 7u) >> 1) ^ (k & 3u)) << 5) +
                                          ((a_cm & 1u) << 4);
-                    *reinterpret_cast<uint4*>(st + off) = hi;
-                    *reinterpret_cast<uint4*>(st + A_BYTES + off) = lo;
+                    sts128(st + off, hi);
+                    sts128(st + A_BYTES + off, lo);
                 }
 #pragma unroll
                 for (int j = 0; j < BK / B_PASS; ++j) {
                     const uint32_t k = b_r + j * B_PASS;
                     float4 b = bv[j];
                     if (has_act && (rb + k) < r1) {
-                        b.x = lrelu(fmaf(b.x, sc.x, sh.x), g.slope); b.y = lrelu(fmaf(b.y, sc.y, sh.y), g.slope);
-                        b.z = lrelu(fmaf(b.z, sc.z, sh.z), g.slope); b.w = lrelu(fmaf(b.w, sc.w, sh.w), g.slope);
+                        b.x = lrelu_max(fmaf(b.x, sc.x, sh.x), g.slope); b.y = lrelu_max(fmaf(b.y, sc.y, sh.y), g.slope);
+                        b.z = lrelu_max(fmaf(b.z, sc.z, sh.z), g.slope); b.w = lrelu_max(fmaf(b.w, sc.w, sh.w), g.slope);
                     }
                     uint4 hi, lo;
                     split_tf32(b.x, hi.x, lo.x); split_tf32(b.y, hi.y, lo.y);
                     split_tf32(b.z, hi.z, lo.z); split_tf32(b.w, hi.w, lo.w);
                     const uint32_t off = b_off0 + (k >> 2) * SBO + (k & 3u) * 128u + ((((b_cm & 7u) >> 1) ^ (k & 3u)) << 5) +
                                          ((b_cm & 1u) << 4);
-                    *reinterpret_cast<uint4*>(st + 2 * A_BYTES + off) = hi;
-                    *reinterpret_cast<uint4*>(st + 2 * A_BYTES + B_BYTES + off) = lo;
+                    sts128(st + 2 * A_BYTES + off, hi);
+                    sts128(st + 2 * A_BYTES + B_BYTES + off, lo);
                 }
                 fence_proxy_async();
                 __syncwarp();
@@ -545,23 +810,38 @@ bool tc_supported_dw(int64_t n, int32_t Cin, int32_t Cout) {
     return n > 0 && Cin >= 64 && Cout >= 64 && Cin % 64 == 0 && Cout % 4 == 0 && Cin <= 4096 && Cout <= 4096;
 }
 
+int64_t tc_gemm_nt_workspace_bytes(int32_t Cin, int32_t Cout) { return 2ll * Cin * Cout * (int64_t)sizeof(float); }
+
+static bool use_v1() {
+    static const bool v = [] { const char* e = getenv("DDMP_TC_V1"); return e && e[0] == '1'; }();
+    return v;
+}
+
 int tc_gemm_xw(const float* X, const int32_t* row_map, const float* scale, const float* shift, float slope,
-               const float* W, float* H, int64_t n, int32_t Cin, int32_t Cout, cudaStream_t st) {
+               const float* W, float* H, void* workspace, int64_t workspace_bytes, int64_t n, int32_t Cin,
+               int32_t Cout, cudaStream_t st) {
     DDMP_REQUIRE(tc_aligned16(X) && tc_aligned16(W) && tc_aligned16(H), "tc_gemm_xw: pointers must be 16-byte aligned");
-    return tc::run_nt(X, row_map, scale, shift, slope, W, H, n, Cout, Cin, st);
+    if (use_v1()) return tc::run_nt(X, row_map, scale, shift, slope, W, H, n, Cout, Cin, st);
+    DDMP_REQUIRE(workspace && tc_aligned16(workspace) && workspace_bytes >= tc_gemm_nt_workspace_bytes(Cin, Cout),
+                 "tc_gemm_xw: workspace too small");
+    return tc::run_nt2(X, row_map, scale, shift, slope, W, 0, workspace, H, n, Cout, Cin, st);
 }
 
-// gX[n,Cin] = dH[n,Cout] * W[Cout,Cin]: the B operand must be K-major, i.e. Wt = W^T [Cin, Cout] (ddmp_transpose).
-int tc_gemm_dx(const float* dH, const float* Wt, float* gX, int64_t n, int32_t Cin, int32_t Cout, cudaStream_t st) {
-    DDMP_REQUIRE(Wt != nullptr, "tc_gemm_dx: needs the transposed weights Wt");
-    DDMP_REQUIRE(tc_aligned16(dH) && tc_aligned16(Wt) && tc_aligned16(gX), "tc_gemm_dx: pointers must be 16-byte aligned");
-    return tc::run_nt(dH, nullptr, nullptr, nullptr, 0.f, Wt, gX, n, Cin, Cout, st);
-}
-
-int transpose(const float* src, float* dst, int32_t rows, int32_t cols, cudaStream_t st) {
-    dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)ceil_div(rows, 32));
-    tc::transpose_kernel<<<grid, dim3(32, 8), 0, st>>>(src, dst, rows, cols);
-    return check_launch("transpose");
+// gX[n,Cin] = dH[n,Cout] * W[Cout,Cin]: B operand (K-major) is W^T, built directly into the swizzled image.
+int tc_gemm_dx(const float* dH, const float* W, float* gX, void* workspace, int64_t workspace_bytes, int64_t n,
+               int32_t Cin, int32_t Cout, cudaStream_t st) {
+    DDMP_REQUIRE(tc_aligned16(dH) && tc_aligned16(W) && tc_aligned16(gX), "tc_gemm_dx: pointers must be 16-byte aligned");
+    DDMP_REQUIRE(workspace && tc_aligned16(workspace) && workspace_bytes >= tc_gemm_nt_workspace_bytes(Cin, Cout),
+                 "tc_gemm_dx: workspace too small");
+    if (use_v1()) {
+        float* wt = reinterpret_cast<float*>(workspace);
+        dim3 grid((unsigned)ceil_div(Cin, 32), (unsigned)ceil_div(Cout, 32));
+        tc::transpose_kernel<<<grid, dim3(32, 8), 0, st>>>(W, wt, Cout, Cin);
+        int rc = check_launch("tc transpose");
+        if (rc) return rc;
+        return tc::run_nt(dH, nullptr, nullptr, nullptr, 0.f, wt, gX, n, Cin, Cout, st);
+    }
+    return tc::run_nt2(dH, nullptr, nullptr, nullptr, 0.f, W, 1, workspace, gX, n, Cin, Cout, st);
 }
 
 int64_t tc_gemm_dw_workspace_bytes(int64_t n, int32_t Cin, int32_t Cout) {

@@ -13,7 +13,7 @@
 namespace ddmp {
 
 template <int C, bool STATS, bool BIAS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, STATS ? 3 : 4)
 spmm_gcn_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const float* __restrict__ w,
                 const float* __restrict__ H, const float* __restrict__ bias, float* __restrict__ Y,
                 float* __restrict__ partials, int64_t n, int rows_per_block) {
@@ -35,11 +35,16 @@ spmm_gcn_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, con
     for (int v = 0; v < NV; ++v) {
         bsum[v] = BIAS ? ldg4(bias + (v * G + lg) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    float4 s[NV], q[NV];
+    // BatchNorm partial sums live in shared memory, one private [2][C] slice per row group (keeping them in
+    // registers costs 8*NV registers and halves the occupancy of the widest instantiation: ncu, profiles/)
+    __shared__ __align__(16) float red[STATS ? GROUPS * 2 * C : 4];
+    float* myred = red + gid * 2 * C;
+    if (STATS) {
 #pragma unroll
-    for (int v = 0; v < NV; ++v) {
-        s[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-        q[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int v = 0; v < NV; ++v) {
+            st4(myred + (v * G + lg) * 4, make_float4(0.f, 0.f, 0.f, 0.f));
+            st4(myred + C + (v * G + lg) * 4, make_float4(0.f, 0.f, 0.f, 0.f));
+        }
     }
 
     for (int64_t r = row0 + gid; r < row_end; r += GROUPS) {
@@ -104,31 +109,26 @@ spmm_gcn_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, con
             }
             st4(yp + (v * G + lg) * 4, o);
             if (STATS) {
-                s[v].x += o.x; s[v].y += o.y; s[v].z += o.z; s[v].w += o.w;
-                q[v].x = fmaf(o.x, o.x, q[v].x); q[v].y = fmaf(o.y, o.y, q[v].y);
-                q[v].z = fmaf(o.z, o.z, q[v].z); q[v].w = fmaf(o.w, o.w, q[v].w);
+                float4 s = *reinterpret_cast<float4*>(myred + (v * G + lg) * 4);
+                float4 q = *reinterpret_cast<float4*>(myred + C + (v * G + lg) * 4);
+                s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
+                q.x = fmaf(o.x, o.x, q.x); q.y = fmaf(o.y, o.y, q.y);
+                q.z = fmaf(o.z, o.z, q.z); q.w = fmaf(o.w, o.w, q.w);
+                st4(myred + (v * G + lg) * 4, s);
+                st4(myred + C + (v * G + lg) * 4, q);
             }
         }
     }
 
     if (STATS) {
         // combine the GROUPS row groups of this CTA channel-wise in a fixed order
-        __shared__ float red[GROUPS * C];
+        __syncthreads();
         float* outp = partials + (int64_t)blockIdx.x * 2 * C;
-#pragma unroll
-        for (int pass = 0; pass < 2; ++pass) {
-#pragma unroll
-            for (int v = 0; v < NV; ++v) {
-                st4(red + gid * C + (v * G + lg) * 4, pass == 0 ? s[v] : q[v]);
-            }
-            __syncthreads();
-            for (int c = threadIdx.x; c < C; c += 256) {
-                float t = 0.f;
+        for (int i = threadIdx.x; i < 2 * C; i += 256) {
+            float t = 0.f;
 #pragma unroll 8
-                for (int g = 0; g < GROUPS; ++g) t += red[g * C + c];
-                outp[pass * C + c] = t;
-            }
-            __syncthreads();
+            for (int g = 0; g < GROUPS; ++g) t += red[g * 2 * C + i];
+            outp[i] = t;
         }
     }
 }

@@ -41,12 +41,23 @@ def spmm_gcn(graph: GcnGraph, H, bias=None, stats=False, transposed=False, out=N
     return (Y, partials) if stats else Y
 
 
+def _gemm_ws(n, Cin, Cout, device, backend):
+    if backend == 1:
+        return None, 0
+    nbytes = int(lib.query("ddmp_gemm_workspace_bytes", n, Cin, Cout))
+    if nbytes == 0:
+        return None, 0
+    return torch.empty(nbytes // 4, dtype=torch.float32, device=device), nbytes
+
+
 def gemm_xw(X, W, row_map=None, scale=None, shift=None, out=None, n=None, backend=None):
     n = X.shape[0] if n is None else n
     Cout, Cin = W.shape
     H = out if out is not None else torch.empty(n, Cout, dtype=torch.float32, device=X.device)
-    lib.call("ddmp_gemm_xw", ptr(X), ptr(row_map), ptr(scale), ptr(shift), SLOPE, ptr(W), ptr(H), n, Cin, Cout,
-             GEMM_BACKEND if backend is None else backend, stream_ptr(X.device))
+    backend = GEMM_BACKEND if backend is None else backend
+    ws, ws_bytes = _gemm_ws(n, Cin, Cout, X.device, backend)
+    lib.call("ddmp_gemm_xw", ptr(X), ptr(row_map), ptr(scale), ptr(shift), SLOPE, ptr(W), ptr(H), ptr(ws), ws_bytes,
+             n, Cin, Cout, backend, stream_ptr(X.device))
     return H
 
 
@@ -55,11 +66,9 @@ def gemm_dx(dH, W, out=None, backend=None):
     Cout, Cin = W.shape
     gX = out if out is not None else torch.empty(n, Cin, dtype=torch.float32, device=dH.device)
     backend = GEMM_BACKEND if backend is None else backend
-    Wt = None
-    if backend != 1 and min(Cin, Cout) >= 64:          # the tensor-core path reads W^T (K-major B operand)
-        Wt = torch.empty(Cin, Cout, dtype=torch.float32, device=dH.device)
-        lib.call("ddmp_transpose", ptr(W), ptr(Wt), Cout, Cin, stream_ptr(dH.device))
-    lib.call("ddmp_gemm_dx", ptr(dH), ptr(W), ptr(Wt), ptr(gX), n, Cin, Cout, backend, stream_ptr(dH.device))
+    ws, ws_bytes = _gemm_ws(n, Cin, Cout, dH.device, backend)
+    lib.call("ddmp_gemm_dx", ptr(dH), ptr(W), ptr(gX), ptr(ws), ws_bytes, n, Cin, Cout, backend,
+             stream_ptr(dH.device))
     return gX
 
 

@@ -95,13 +95,14 @@ int ddmp_colsum_partials(const float* X, float* partials, int64_t n, int32_t C, 
  * gather from the caller's numbering into the space-filling-curve order).
  * [ref: GCNConv.lin at util/networks.py:51-62 — cuBLAS SGEMM] */
 int ddmp_gemm_xw(const float* X, const int32_t* row_map, const float* scale, const float* shift, float slope,
-                 const float* W, float* H, int64_t n, int32_t Cin, int32_t Cout, int backend, void* stream);
-/* gX[n,Cin] = dH[n,Cout] * W[Cout,Cin].  Wt = W^T [Cin,Cout] (ddmp_transpose) is what the tensor-core path reads
- * (K-major B operand); with Wt == NULL the FFMA kernel is used. */
-int ddmp_gemm_dx(const float* dH, const float* W, const float* Wt, float* gX, int64_t n, int32_t Cin, int32_t Cout,
-                 int backend, void* stream);
-/* dst[cols,rows] = src[rows,cols]^T (weights only; a few hundred KB). */
-int ddmp_transpose(const float* src, float* dst, int32_t rows, int32_t cols, void* stream);
+                 const float* W, float* H, void* workspace, int64_t workspace_bytes, int64_t n, int32_t Cin,
+                 int32_t Cout, int backend, void* stream);
+/* scratch the tensor-core path of gemm_xw / gemm_dx needs for the pre-split, pre-swizzled weight image (0 when the
+ * shape runs on the FFMA kernel; with workspace == NULL the FFMA kernel is used). */
+int64_t ddmp_gemm_workspace_bytes(int64_t n, int32_t Cin, int32_t Cout);
+/* gX[n,Cin] = dH[n,Cout] * W[Cout,Cin]. */
+int ddmp_gemm_dx(const float* dH, const float* W, float* gX, void* workspace, int64_t workspace_bytes, int64_t n,
+                 int32_t Cin, int32_t Cout, int backend, void* stream);
 /* dW[Cout,Cin] = dH[n,Cout]^T * act(X)[n,Cin]; deterministic split-K over rows through `workspace`. */
 int64_t ddmp_gemm_dw_workspace_bytes(int64_t n, int32_t Cin, int32_t Cout);
 int ddmp_gemm_dw(const float* dH, const float* X, const int32_t* row_map, const float* scale, const float* shift,

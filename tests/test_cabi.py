@@ -37,7 +37,7 @@ def test_header_declares_and_library_exports(built):
 def test_host_only_queries(built):
     assert _lib.lib.query("ddmp_version") >= 100
     assert _lib.lib.query("ddmp_rows_per_block", 512) == 128
-    assert _lib.lib.query("ddmp_rows_per_block", 32) == 1024
+    assert _lib.lib.query("ddmp_rows_per_block", 32) == 256
     assert _lib.lib.query("ddmp_num_row_blocks", 1000, 512) == 8
     assert _lib.lib.query("ddmp_loss_scratch_bytes") >= 8192
     assert _lib.lib.query("ddmp_gemm_dw_workspace_bytes", 100000, 256, 512) > 0
