@@ -72,7 +72,9 @@ def product_masks(net_d):
     perm = torch.from_numpy(net_d.last_graph.perm_host)
     masks = []
     for y, st in net_d.taps:
-        z = (y * st[2] + st[3]).cpu() if st is not None else y.cpu()      # last entry: head hidden layer
+        # float64 so that the sign equals the sign of the kernels' fmaf(y, scale, shift) (a separately rounded
+        # multiply and add can differ from the fused result when |z| ~ 1e-7); last entry: head hidden layer
+        z = (y.double() * st[2].double() + st[3].double()).cpu() if st is not None else y.cpu()
         m = torch.empty_like(z, dtype=torch.bool)
         m[perm] = z > 0
         masks.append(m)
