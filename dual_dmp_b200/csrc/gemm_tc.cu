@@ -12,6 +12,8 @@
 // tcgen05.commit releases a stage / publishes the accumulator.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace ddmp {
@@ -409,50 +411,70 @@ __global__ void __launch_bounds__(kV2Threads, 1) tc_gemm_nt2_kernel(const Nt2Arg
     const uint32_t smem_base = smem_u32(smem);
 
     if (warp < kProducerWarps) {
-        // ===== A producers =====
+        // ===== A producers: flattened (tile, k-block) iteration space, global loads issued two iterations ahead =====
         const int t = threadIdx.x;
         const uint32_t c = t & 7;
         const bool has_act = g.scale != nullptr;
-        uint32_t it = 0;
-        for (int64_t tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+        constexpr int NJ = BM * 8 / kProducerThreads;        // float4 per thread per k-block
+        const int64_t my_tiles = (g.num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+        const int64_t total = my_tiles * num_kb;
+        float4 av[2][NJ];
+        bool ok[2][NJ];
+        auto issue = [&](int64_t itx, auto slot_c) {
+            constexpr int slot = decltype(slot_c)::value;      // compile-time slot keeps av[][] in registers
+            if (itx >= total) return;
+            const int64_t tile = blockIdx.x + (itx / num_kb) * gridDim.x;
+            const int kb = (int)(itx % num_kb);
             const int64_t m0 = (tile / g.tiles_n) * BM;
-            int64_t src_row[BM * 8 / kProducerThreads];
+            const int k0 = kb * BK + c * 4;
 #pragma unroll
-            for (int j = 0; j < BM * 8 / kProducerThreads; ++j) {
+            for (int j = 0; j < NJ; ++j) {
                 const int64_t m = m0 + (t >> 3) + j * (kProducerThreads / 8);
-                src_row[j] = (m < g.M) ? (g.a_map ? (int64_t)__ldg(g.a_map + m) : m) : -1;
-            }
-            for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
-                const int k0 = kb * BK + c * 4;
-                float4 av[BM * 8 / kProducerThreads];
-#pragma unroll
-                for (int j = 0; j < BM * 8 / kProducerThreads; ++j)
-                    av[j] = (src_row[j] >= 0) ? ldg4(g.A + src_row[j] * g.K + k0) : make_float4(0.f, 0.f, 0.f, 0.f);
-                float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (has_act) { sc = ldg4(g.scale + k0); sh = ldg4(g.shift + k0); }
-                mbar_wait(empty_bar + s, ph ^ 1u);
-                const uint32_t st = smem_base + s * STAGE_BYTES;
-#pragma unroll
-                for (int j = 0; j < BM * 8 / kProducerThreads; ++j) {
-                    const uint32_t row = (t >> 3) + j * (kProducerThreads / 8);
-                    float4 a = av[j];
-                    if (has_act && src_row[j] >= 0) {
-                        a.x = lrelu_max(fmaf(a.x, sc.x, sh.x), g.slope); a.y = lrelu_max(fmaf(a.y, sc.y, sh.y), g.slope);
-                        a.z = lrelu_max(fmaf(a.z, sc.z, sh.z), g.slope); a.w = lrelu_max(fmaf(a.w, sc.w, sh.w), g.slope);
-                    }
-                    uint4 hi, lo;
-                    split_tf32(a.x, hi.x, lo.x); split_tf32(a.y, hi.y, lo.y);
-                    split_tf32(a.z, hi.z, lo.z); split_tf32(a.w, hi.w, lo.w);
-                    const uint32_t off = sw128(row, c);
-                    sts128(st + off, hi);
-                    sts128(st + A_BYTES + off, lo);
+                ok[slot][j] = m < g.M;
+                if (ok[slot][j]) {
+                    const int64_t src = g.a_map ? (int64_t)__ldg(g.a_map + m) : m;
+                    av[slot][j] = ldg4(g.A + src * g.K + k0);
+                } else {
+                    av[slot][j] = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(full_bar + s);
             }
+        };
+        using S0 = std::integral_constant<int, 0>;
+        using S1 = std::integral_constant<int, 1>;
+        issue(0, S0{});
+        issue(1, S1{});
+        auto step = [&](int64_t it, auto slot_c) {
+            constexpr int slot = decltype(slot_c)::value;
+            const int s = (int)(it % STAGES);
+            const uint32_t ph = (uint32_t)((it / STAGES) & 1);
+            const int k0 = (int)(it % num_kb) * BK + c * 4;
+            float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (has_act) { sc = ldg4(g.scale + k0); sh = ldg4(g.shift + k0); }
+            mbar_wait(empty_bar + s, ph ^ 1u);
+            const uint32_t st = smem_base + s * STAGE_BYTES;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                const uint32_t row = (t >> 3) + j * (kProducerThreads / 8);
+                float4 a = av[slot][j];
+                if (has_act && ok[slot][j]) {
+                    a.x = lrelu_max(fmaf(a.x, sc.x, sh.x), g.slope); a.y = lrelu_max(fmaf(a.y, sc.y, sh.y), g.slope);
+                    a.z = lrelu_max(fmaf(a.z, sc.z, sh.z), g.slope); a.w = lrelu_max(fmaf(a.w, sc.w, sh.w), g.slope);
+                }
+                uint4 hi, lo;
+                split_tf32(a.x, hi.x, lo.x); split_tf32(a.y, hi.y, lo.y);
+                split_tf32(a.z, hi.z, lo.z); split_tf32(a.w, hi.w, lo.w);
+                const uint32_t off = sw128(row, c);
+                sts128(st + off, hi);
+                sts128(st + A_BYTES + off, lo);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full_bar + s);
+            issue(it + 2, slot_c);                            // refill the slot just consumed
+        };
+        for (int64_t it = 0; it < total; it += 2) {
+            step(it, S0{});
+            if (it + 1 < total) step(it + 1, S1{});
         }
     } else if (warp == 8) {
         // ===== MMA issuer =====
@@ -653,11 +675,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_tn_kernel(const TnArgs g)
             float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
             if (has_act) { sc = ldg4(g.scale + n0 + b_cm * 4); sh = ldg4(g.shift + n0 + b_cm * 4); }
             const uint32_t a_off0 = (a_cm / 8) * LBO, b_off0 = (b_cm / 8) * LBO;
-            for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
+            float4 av[BK / A_PASS], bv[BK / B_PASS];
+            // global loads of k-block kb+1 are issued right after the stores of kb, so their latency overlaps the
+            // wait for the next free stage (the MMA of an earlier block) instead of being exposed every iteration
+            auto issue = [&](int kb) {
+                if (kb >= num_kb) return;
                 const int64_t rb = r0 + (int64_t)kb * BK;
-                float4 av[BK / A_PASS], bv[BK / B_PASS];
 #pragma unroll
                 for (int j = 0; j < BK / A_PASS; ++j) {
                     const int64_t r = rb + a_r + j * A_PASS;
@@ -668,6 +691,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_tn_kernel(const TnArgs g)
                     const int64_t r = rb + b_r + j * B_PASS;
                     bv[j] = (r < r1) ? ldg4(g.B + r * g.N + n0 + b_cm * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
+            };
+            issue(0);
+            for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                const int64_t rb = r0 + (int64_t)kb * BK;
                 mbar_wait(empty_bar + s, ph ^ 1u);
                 const uint32_t st = smem_base + s * STAGE_BYTES;
 #pragma unroll
@@ -700,6 +729,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_tn_kernel(const TnArgs g)
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(full_bar + s);
+                issue(kb + 1);
             }
             // ---- epilogue of this item ----
             mbar_wait(accum_bar, item_no & 1u);
