@@ -353,6 +353,14 @@ struct Nt2Args {
 };
 
 // W [N,K] (or, transposed, W^T given as [K,N]) -> image; one thread per (n, 16-byte chunk of K)
+// byte offset of (row r, 16-byte chunk c) in a K-major tile with rows of KB*4 bytes: SWIZZLE_128B (KB=32) / _64B (KB=16)
+template <int KB>
+__device__ __forceinline__ uint32_t swz(uint32_t r, uint32_t c) {
+    if constexpr (KB == 32) return r * 128u + ((c ^ (r & 7u)) << 4);
+    else return r * 64u + ((c ^ ((r >> 1) & 3u)) << 4);
+}
+
+template <int KB>
 __global__ void tc_prep_b_kernel(const float* __restrict__ W, int transposed, uint8_t* __restrict__ img, int N, int K,
                                  int BN) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -368,18 +376,23 @@ __global__ void tc_prep_b_kernel(const float* __restrict__ W, int transposed, ui
     }
     uint4 hi, lo;
     split_tf32(v.x, hi.x, lo.x); split_tf32(v.y, hi.y, lo.y); split_tf32(v.z, hi.z, lo.z); split_tf32(v.w, hi.w, lo.w);
-    const int n_tile = n / BN, r = n % BN, kb = k / BK, c = (k % BK) / 4;
-    const int num_kb = K / BK;
-    const int64_t base = ((int64_t)n_tile * num_kb + kb) * 2 * ((int64_t)BN * 128);
-    const uint32_t off = sw128((uint32_t)r, (uint32_t)c);
+    const int n_tile = n / BN, r = n % BN, kb = k / KB, c = (k % KB) / 4;
+    const int num_kb = K / KB;
+    const int64_t base = ((int64_t)n_tile * num_kb + kb) * 2 * ((int64_t)BN * KB * 4);
+    const uint32_t off = swz<KB>((uint32_t)r, (uint32_t)c);
     *reinterpret_cast<uint4*>(img + base + off) = hi;
-    *reinterpret_cast<uint4*>(img + base + (int64_t)BN * 128 + off) = lo;
+    *reinterpret_cast<uint4*>(img + base + (int64_t)BN * KB * 4 + off) = lo;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool DEEP, int KB>
 __global__ void __launch_bounds__(kV2Threads, 1) tc_gemm_nt2_kernel(const Nt2Args g) {
-    constexpr uint32_t A_BYTES = BM * 128;
-    constexpr uint32_t B_BYTES = BN * 128;
+    constexpr int BK = KB;                           // shadows the file-level BK inside this kernel
+    constexpr uint32_t ROW_BYTES = KB * 4;           // 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B)
+    constexpr uint32_t CPR = KB / 4;                 // 16-byte chunks per row
+    constexpr uint32_t SBO = 8 * ROW_BYTES;          // 8-row swizzle atom
+    constexpr uint32_t LTYPE = (KB == 32) ? 2u : 4u; // descriptor layout type
+    constexpr uint32_t A_BYTES = BM * ROW_BYTES;
+    constexpr uint32_t B_BYTES = BN * ROW_BYTES;
     constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
     constexpr uint32_t TMEM_COLS = 2 * BN;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -413,68 +426,120 @@ __global__ void __launch_bounds__(kV2Threads, 1) tc_gemm_nt2_kernel(const Nt2Arg
     if (warp < kProducerWarps) {
         // ===== A producers: flattened (tile, k-block) iteration space, global loads issued two iterations ahead =====
         const int t = threadIdx.x;
-        const uint32_t c = t & 7;
+        const uint32_t c = t % CPR;
         const bool has_act = g.scale != nullptr;
-        constexpr int NJ = BM * 8 / kProducerThreads;        // float4 per thread per k-block
-        const int64_t my_tiles = (g.num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
-        const int64_t total = my_tiles * num_kb;
-        float4 av[2][NJ];
-        bool ok[2][NJ];
-        auto issue = [&](int64_t itx, auto slot_c) {
-            constexpr int slot = decltype(slot_c)::value;      // compile-time slot keeps av[][] in registers
-            if (itx >= total) return;
-            const int64_t tile = blockIdx.x + (itx / num_kb) * gridDim.x;
-            const int kb = (int)(itx % num_kb);
-            const int64_t m0 = (tile / g.tiles_n) * BM;
-            const int k0 = kb * BK + c * 4;
+        constexpr int NJ = BM * CPR / kProducerThreads;      // float4 per thread per k-block
+        constexpr int RPP = kProducerThreads / CPR;          // rows covered by one pass of the producer threads
+        if constexpr (!DEEP) {
+            // loads of a k-block are issued at the top of its own iteration (one iteration of prefetch over the wait)
+            uint32_t it = 0;
+            for (int64_t tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+                const int64_t m0 = (tile / g.tiles_n) * BM;
+                int64_t src_row[NJ];
 #pragma unroll
-            for (int j = 0; j < NJ; ++j) {
-                const int64_t m = m0 + (t >> 3) + j * (kProducerThreads / 8);
-                ok[slot][j] = m < g.M;
-                if (ok[slot][j]) {
-                    const int64_t src = g.a_map ? (int64_t)__ldg(g.a_map + m) : m;
-                    av[slot][j] = ldg4(g.A + src * g.K + k0);
-                } else {
-                    av[slot][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int j = 0; j < NJ; ++j) {
+                    const int64_t m = m0 + (t / CPR) + j * RPP;
+                    src_row[j] = (m < g.M) ? (g.a_map ? (int64_t)__ldg(g.a_map + m) : m) : -1;
+                }
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    const int k0 = kb * BK + c * 4;
+                    float4 av[NJ];
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j)
+                        av[j] = (src_row[j] >= 0) ? ldg4(g.A + src_row[j] * g.K + k0) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (has_act) { sc = ldg4(g.scale + k0); sh = ldg4(g.shift + k0); }
+                    mbar_wait(empty_bar + s, ph ^ 1u);
+                    const uint32_t st = smem_base + s * STAGE_BYTES;
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) {
+                        const uint32_t row = (t / CPR) + j * RPP;
+                        float4 a = av[j];
+                        if (has_act && src_row[j] >= 0) {
+                            a.x = lrelu_max(fmaf(a.x, sc.x, sh.x), g.slope); a.y = lrelu_max(fmaf(a.y, sc.y, sh.y), g.slope);
+                            a.z = lrelu_max(fmaf(a.z, sc.z, sh.z), g.slope); a.w = lrelu_max(fmaf(a.w, sc.w, sh.w), g.slope);
+                        }
+                        uint4 hi, lo;
+                        split_tf32(a.x, hi.x, lo.x); split_tf32(a.y, hi.y, lo.y);
+                        split_tf32(a.z, hi.z, lo.z); split_tf32(a.w, hi.w, lo.w);
+                        const uint32_t off = swz<KB>(row, c);
+                        sts128(st + off, hi);
+                        sts128(st + A_BYTES + off, lo);
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(full_bar + s);
                 }
             }
-        };
-        using S0 = std::integral_constant<int, 0>;
-        using S1 = std::integral_constant<int, 1>;
-        issue(0, S0{});
-        issue(1, S1{});
-        auto step = [&](int64_t it, auto slot_c) {
-            constexpr int slot = decltype(slot_c)::value;
-            const int s = (int)(it % STAGES);
-            const uint32_t ph = (uint32_t)((it / STAGES) & 1);
-            const int k0 = (int)(it % num_kb) * BK + c * 4;
-            float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (has_act) { sc = ldg4(g.scale + k0); sh = ldg4(g.shift + k0); }
-            mbar_wait(empty_bar + s, ph ^ 1u);
-            const uint32_t st = smem_base + s * STAGE_BYTES;
-#pragma unroll
-            for (int j = 0; j < NJ; ++j) {
-                const uint32_t row = (t >> 3) + j * (kProducerThreads / 8);
-                float4 a = av[slot][j];
-                if (has_act && ok[slot][j]) {
-                    a.x = lrelu_max(fmaf(a.x, sc.x, sh.x), g.slope); a.y = lrelu_max(fmaf(a.y, sc.y, sh.y), g.slope);
-                    a.z = lrelu_max(fmaf(a.z, sc.z, sh.z), g.slope); a.w = lrelu_max(fmaf(a.w, sc.w, sh.w), g.slope);
+        } else {
+            const int64_t my_tiles = (g.num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+            const int64_t total = my_tiles * num_kb;
+            float4 av[2][NJ];
+            bool ok[2][NJ];
+            // prefetch cursor (advanced incrementally: no divisions in the loop)
+            int64_t pf_tile = blockIdx.x;
+            int pf_kb = 0;
+            int64_t pf_left = total;
+            auto issue = [&](auto slot_c) {
+                constexpr int slot = decltype(slot_c)::value;      // compile-time slot keeps av[][] in registers
+                if (pf_left <= 0) return;
+                const int64_t m0 = (int64_t)((uint32_t)pf_tile / (uint32_t)g.tiles_n) * BM;   // num_tiles < 2^31
+                const int k0 = pf_kb * BK + c * 4;
+    #pragma unroll
+                for (int j = 0; j < NJ; ++j) {
+                    const int64_t m = m0 + (t / CPR) + j * RPP;
+                    ok[slot][j] = m < g.M;
+                    if (ok[slot][j]) {
+                        const int64_t src = g.a_map ? (int64_t)__ldg(g.a_map + m) : m;
+                        av[slot][j] = ldg4(g.A + src * g.K + k0);
+                    } else {
+                        av[slot][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
                 }
-                uint4 hi, lo;
-                split_tf32(a.x, hi.x, lo.x); split_tf32(a.y, hi.y, lo.y);
-                split_tf32(a.z, hi.z, lo.z); split_tf32(a.w, hi.w, lo.w);
-                const uint32_t off = sw128(row, c);
-                sts128(st + off, hi);
-                sts128(st + A_BYTES + off, lo);
+                --pf_left;
+                if (++pf_kb == num_kb) { pf_kb = 0; pf_tile += gridDim.x; }
+            };
+            using S0 = std::integral_constant<int, 0>;
+            using S1 = std::integral_constant<int, 1>;
+            issue(S0{});
+            issue(S1{});
+            int s = 0, kb_cur = 0;
+            uint32_t ph = 0;
+            auto step = [&](auto slot_c) {
+                constexpr int slot = decltype(slot_c)::value;
+                const int k0 = kb_cur * BK + c * 4;
+                float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (has_act) { sc = ldg4(g.scale + k0); sh = ldg4(g.shift + k0); }
+                mbar_wait(empty_bar + s, ph ^ 1u);
+                const uint32_t st = smem_base + s * STAGE_BYTES;
+    #pragma unroll
+                for (int j = 0; j < NJ; ++j) {
+                    const uint32_t row = (t / CPR) + j * RPP;
+                    float4 a = av[slot][j];
+                    if (has_act && ok[slot][j]) {
+                        a.x = lrelu_max(fmaf(a.x, sc.x, sh.x), g.slope); a.y = lrelu_max(fmaf(a.y, sc.y, sh.y), g.slope);
+                        a.z = lrelu_max(fmaf(a.z, sc.z, sh.z), g.slope); a.w = lrelu_max(fmaf(a.w, sc.w, sh.w), g.slope);
+                    }
+                    uint4 hi, lo;
+                    split_tf32(a.x, hi.x, lo.x); split_tf32(a.y, hi.y, lo.y);
+                    split_tf32(a.z, hi.z, lo.z); split_tf32(a.w, hi.w, lo.w);
+                    const uint32_t off = swz<KB>(row, c);
+                    sts128(st + off, hi);
+                    sts128(st + A_BYTES + off, lo);
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full_bar + s);
+                if (++s == STAGES) { s = 0; ph ^= 1u; }
+                if (++kb_cur == num_kb) kb_cur = 0;
+                issue(slot_c);                                    // refill the slot just consumed
+            };
+            for (int64_t it = 0; it < total; it += 2) {
+                step(S0{});
+                if (it + 1 < total) step(S1{});
             }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(full_bar + s);
-            issue(it + 2, slot_c);                            // refill the slot just consumed
-        };
-        for (int64_t it = 0; it < total; it += 2) {
-            step(it, S0{});
-            if (it + 1 < total) step(it + 1, S1{});
         }
     } else if (warp == 8) {
         // ===== MMA issuer =====
@@ -495,10 +560,10 @@ __global__ void __launch_bounds__(kV2Threads, 1) tc_gemm_nt2_kernel(const Nt2Arg
 #pragma unroll
                     for (int ks = 0; ks < BK / UMMA_K; ++ks) {
                         const uint32_t koff = ks * UMMA_K * 4;
-                        const uint64_t a_hi = make_desc(sa + koff, 16, 1024);
-                        const uint64_t a_lo = make_desc(sa + A_BYTES + koff, 16, 1024);
-                        const uint64_t b_hi = make_desc(sa + 2 * A_BYTES + koff, 16, 1024);
-                        const uint64_t b_lo = make_desc(sa + 2 * A_BYTES + B_BYTES + koff, 16, 1024);
+                        const uint64_t a_hi = make_desc(sa + koff, 16, SBO, LTYPE);
+                        const uint64_t a_lo = make_desc(sa + A_BYTES + koff, 16, SBO, LTYPE);
+                        const uint64_t b_hi = make_desc(sa + 2 * A_BYTES + koff, 16, SBO, LTYPE);
+                        const uint64_t b_lo = make_desc(sa + 2 * A_BYTES + B_BYTES + koff, 16, SBO, LTYPE);
                         umma_tf32(d_tmem, a_lo, b_hi, idesc, (kb | ks) != 0);
                         umma_tf32(d_tmem, a_hi, b_lo, idesc, 1);
                         umma_tf32(d_tmem, a_hi, b_hi, idesc, 1);
@@ -561,18 +626,32 @@ __global__ void __launch_bounds__(kV2Threads, 1) tc_gemm_nt2_kernel(const Nt2Arg
     }
 }
 
-template <int BN, int STAGES>
-static int launch_nt2(const Nt2Args& g, cudaStream_t st) {
-    constexpr size_t smem = (size_t)STAGES * (2 * BM * 128 + 2 * BN * 128) + 1024 + 256;
+template <int BN, int STAGES, bool DEEP, int KB>
+static int launch_nt2_impl(const Nt2Args& g, cudaStream_t st) {
+    constexpr size_t smem = (size_t)STAGES * (2 * BM * KB * 4 + 2 * BN * KB * 4) + 1024 + 256;
     static bool configured = false;
     if (!configured) {
-        DDMP_CUDA(cudaFuncSetAttribute(tc_gemm_nt2_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem));
+        DDMP_CUDA(cudaFuncSetAttribute(tc_gemm_nt2_kernel<BN, STAGES, DEEP, KB>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     const int64_t grid = g.num_tiles < kNumSMs ? g.num_tiles : kNumSMs;
-    tc_gemm_nt2_kernel<BN, STAGES><<<(unsigned)grid, kV2Threads, smem, st>>>(g);
+    tc_gemm_nt2_kernel<BN, STAGES, DEEP, KB><<<(unsigned)grid, kV2Threads, smem, st>>>(g);
     return check_launch("tc_gemm_nt2");
+}
+// K-block: 32 (SWIZZLE_128B, default) or 16 (SWIZZLE_64B, twice the stages; DDMP_TC_BK=16).  Measured on B200
+// (profiles/gemm_ab_r1.txt): 32 is 10-15 % faster, and the 2-deep register prefetch (DDMP_TC_DEEP=1) is 8 % slower
+// than issuing the loads at the top of the iteration -> the kernel is throughput-, not latency-bound.
+static int nt2_kb() {
+    static const int v = [] { const char* e = getenv("DDMP_TC_BK"); return (e && atoi(e) == 16) ? 16 : 32; }();
+    return v;
+}
+template <int BN, int STAGES32>
+static int launch_nt2(const Nt2Args& g, cudaStream_t st) {
+    static const bool deep = [] { const char* e = getenv("DDMP_TC_DEEP"); return e && e[0] == '1'; }();
+    if (nt2_kb() == 32)
+        return deep ? launch_nt2_impl<BN, STAGES32, true, 32>(g, st) : launch_nt2_impl<BN, STAGES32, false, 32>(g, st);
+    return deep ? launch_nt2_impl<BN, 2 * STAGES32, true, 16>(g, st) : launch_nt2_impl<BN, 2 * STAGES32, false, 16>(g, st);
 }
 
 // B = W [N,K] row-major (transposed == 0) or B = W^T where W is [K,N] row-major (transposed == 1)
@@ -582,13 +661,15 @@ static int run_nt2(const float* A, const int* a_map, const float* scale, const f
     const int BN = (N % 256 == 0) ? 256 : ((N % 128 == 0) ? 128 : 64);
     uint8_t* img = reinterpret_cast<uint8_t*>(workspace);
     const int64_t chunks = (int64_t)N * (K / 4);
-    tc_prep_b_kernel<<<(unsigned)ceil_div(chunks, 256), 256, 0, st>>>(W, transposed, img, N, K, BN);
+    if (nt2_kb() == 32) tc_prep_b_kernel<32><<<(unsigned)ceil_div(chunks, 256), 256, 0, st>>>(W, transposed, img, N, K, BN);
+    else tc_prep_b_kernel<16><<<(unsigned)ceil_div(chunks, 256), 256, 0, st>>>(W, transposed, img, N, K, BN);
     int rc = check_launch("tc_prep_b");
     if (rc) return rc;
     Nt2Args g{};
     g.A = A; g.Bimg = img; g.C = C; g.a_map = a_map; g.scale = scale; g.shift = shift; g.slope = slope;
     g.M = M; g.N = N; g.K = K; g.tiles_n = N / BN;
     g.num_tiles = ceil_div(M, BM) * g.tiles_n;
+    DDMP_REQUIRE(g.num_tiles < (1ll << 31), "tc gemm: too many tiles");
     if (BN == 256) return launch_nt2<256, 2>(g, st);
     if (BN == 128) return launch_nt2<128, 3>(g, st);
     return launch_nt2<64, 4>(g, st);
