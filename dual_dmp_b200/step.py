@@ -1,0 +1,91 @@
+"""The training iteration of the reference drivers as one object.
+
+``DualStep.step(epoch)`` is reference main.py:88-110 / main4real.py:53-70: zero_grad, PosNet and NormalNet forward, the
+five losses (``loss_norm2 *= 0`` while epoch <= 100), weighted sum, backward, ``clip_grad_norm_`` on NormalNet, two
+Adam steps.  Inputs and targets are kept resident on the device (the reference re-uploads ~100 MB per step at 1M
+faces), nothing synchronises the host, and the whole iteration is captured into CUDA graphs (one for the BNF warm-up
+phase, one for the rest, sharing a memory pool) so a step is a single graph launch: at fandisk size the eager step
+is bound by ~700 Python-side launches (8.5 ms), the replayed one by the GPU.
+
+The numerics are those of the eager drop-in path: the same autograd Functions and kernels are what gets captured.
+"""
+from __future__ import annotations
+
+import copy
+
+import torch
+
+from .util import loss as L
+
+
+class DualStep:
+    def __init__(self, posnet, normnet, dataset, n_mesh, k=(3.0, 4.0, 4.0, 4.0, 1.0), bnfloop=1, pos_lr=0.01,
+                 norm_lr=0.01, grad_clip=0.8, bnf_warmup_epochs=100, capture=True):
+        dev = torch.device(posnet.device)
+        if dev.type != "cuda":
+            raise RuntimeError("DualStep runs on CUDA only (dual_dmp_b200 has no CPU path)")
+        self.device = dev
+        self.posnet, self.normnet, self.mesh = posnet, normnet, n_mesh
+        self.k, self.bnfloop, self.grad_clip = tuple(float(x) for x in k), int(bnfloop), float(grad_clip)
+        self.bnf_warmup_epochs = int(bnf_warmup_epochs)
+        self.dataset = copy.copy(dataset).to(dev)                       # resident inputs
+        self.tgt_vs = torch.from_numpy(n_mesh.vs).to(dev)               # float64 targets, like the reference
+        self.tgt_fn = torch.from_numpy(n_mesh.fn).to(dev)
+        self.capture = bool(capture)
+        self.opt_pos = torch.optim.Adam(posnet.parameters(), lr=pos_lr, capturable=self.capture)
+        self.opt_norm = torch.optim.Adam(normnet.parameters(), lr=norm_lr, capturable=self.capture)
+        self._graphs: dict = {}
+        self._static_loss: dict = {}
+        self._eager_calls = 0
+        self.pos = None      # outputs of the most recent step (static tensors when captured)
+        self.norm = None
+
+    # ---- the loop body (reference main.py:88-110) ------------------------------------------------------------------
+    def _body(self, bnf_off: bool) -> torch.Tensor:
+        k = self.k
+        self.posnet.train()
+        self.normnet.train()
+        self.opt_pos.zero_grad(set_to_none=True)
+        self.opt_norm.zero_grad(set_to_none=True)
+        pos = self.posnet(self.dataset)
+        l1 = L.pos_rec_loss(pos, self.tgt_vs)
+        l2 = L.mesh_laplacian_loss(pos, self.mesh)
+        nrm = self.normnet(self.dataset)
+        l3 = L.norm_rec_loss(nrm, self.tgt_fn)
+        l4, _ = L.fn_bnf_loss(pos, nrm, self.mesh, loop=self.bnfloop)
+        if bnf_off:
+            l4 = l4 * 0.0                   # still computed and back-propagated, exactly like the reference (:101-102)
+        l5 = L.pos_norm_loss(pos, nrm, self.mesh)
+        loss = k[0] * l1 + k[1] * l2 + k[2] * l3 + k[3] * l4 + k[4] * l5
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(self.normnet.parameters(), self.grad_clip)
+        self.opt_pos.step()
+        self.opt_norm.step()
+        self.pos, self.norm = pos.detach(), nrm.detach()
+        return loss.detach()
+
+    def _capture(self, bnf_off: bool) -> None:
+        g = torch.cuda.CUDAGraph()
+        pool = next(iter(self._graphs.values())).pool() if self._graphs else None
+        with torch.cuda.graph(g, pool=pool):
+            self._static_loss[bnf_off] = self._body(bnf_off)
+        self._graphs[bnf_off] = g
+
+    def step(self, epoch: int) -> torch.Tensor:
+        """one training iteration; returns the (device, float64) loss without synchronising"""
+        bnf_off = epoch <= self.bnf_warmup_epochs
+        if not self.capture:
+            return self._body(bnf_off)
+        if bnf_off not in self._graphs:
+            if self._eager_calls < 3:
+                # warm-up on a side stream (graph/index caches, optimizer state, allocator) before capturing
+                self._eager_calls += 1
+                s = torch.cuda.Stream(self.device)
+                s.wait_stream(torch.cuda.current_stream(self.device))
+                with torch.cuda.stream(s):
+                    loss = self._body(bnf_off)
+                torch.cuda.current_stream(self.device).wait_stream(s)
+                return loss
+            self._capture(bnf_off)
+        self._graphs[bnf_off].replay()
+        return self._static_loss[bnf_off]

@@ -5,7 +5,7 @@ set -u
 mkdir -p gpurun_out
 rm -f gpurun_out/parity.log
 nvidia-smi --query-gpu=name,driver_version,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
-for f in test_gpu_ops test_gpu_losses test_gpu_nets; do
+for f in test_gpu_ops test_gpu_losses test_gpu_nets test_gpu_large; do
   timeout 900 python -m pytest tests/$f.py -m gpu -q --tb=short -p no:cacheprovider > gpurun_out/$f.log 2>&1
   echo "$f exit=$?" >> gpurun_out/summary.txt
   tail -n 3 gpurun_out/$f.log

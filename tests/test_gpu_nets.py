@@ -179,3 +179,35 @@ def test_eval_mode_uses_running_statistics():
     pr.eval(); pd.eval()
     with torch.no_grad():
         assert rel_err(pd(ds), pr(ds)) < 1e-4
+
+
+def test_dual_step_cuda_graph_matches_eager_and_oracle():
+    """dual_dmp_b200.step.DualStep (reference main.py:88-110 as one object): the CUDA-graph replayed iteration gives
+    the same losses as the eager drop-in loop, crosses the epoch-100 BNF switch, and tracks the CPU oracle"""
+    import copy
+    from dual_dmp_b200.step import DualStep
+    from dual_dmp_b200.util.datamaker import dataset_from_meshes
+    from oracle import step_ref
+    n_mesh, s_mesh, _ = small_case("ico", 10)
+    ds = dataset_from_meshes(n_mesh, s_mesh)
+    pr, nr, pd, nd = _pair(4)
+    pd2, nd2 = copy.deepcopy(pd), copy.deepcopy(nd)
+    graph_step = DualStep(pd, nd, ds, n_mesh, bnfloop=2, capture=True)
+    eager_step = DualStep(pd2, nd2, ds, n_mesh, bnfloop=2, capture=False)
+    opt_r = (torch.optim.Adam(pr.parameters(), lr=0.01), torch.optim.Adam(nr.parameters(), lr=0.01))
+    epochs = [97, 98, 99, 100, 101, 102, 103]           # 3 eager warm-ups, capture (bnf off), switch, capture (bnf on)
+    lg, le, lo = [], [], []
+    for ep in epochs:
+        lg.append(graph_step.step(ep).clone())
+        le.append(eager_step.step(ep).clone())
+        lo.append(step_ref.train_step(pr, nr, opt_r[0], opt_r[1], ds, n_mesh, bnfloop=2, epoch=ep)[0])
+    torch.cuda.synchronize()
+    assert len(graph_step._graphs) == 2
+    lg, le, lo = [float(x) for x in lg], [float(x) for x in le], [float(x) for x in lo]
+    report("dual_step losses graph/eager/oracle", (lg, le, lo))
+    for a, b in zip(lg, le):
+        assert abs(a - b) <= 1e-4 * abs(b), (lg, le)
+    assert abs(lg[0] - lo[0]) <= 1e-4 * abs(lo[0])
+    for a, b in zip(lg, lo):                            # later iterations: Adam amplifies rounding, track loosely
+        assert abs(a - b) <= 5e-2 * abs(b), (lg, lo)
+    assert graph_step.pos.shape == (len(n_mesh.vs), 3) and torch.isfinite(graph_step.pos).all()
