@@ -205,8 +205,9 @@ def test_dual_step_cuda_graph_matches_eager_and_oracle():
     assert len(graph_step._graphs) == 2
     lg, le, lo = [float(x) for x in lg], [float(x) for x in le], [float(x) for x in lo]
     report("dual_step losses graph/eager/oracle", (lg, le, lo))
-    for a, b in zip(lg, le):
-        assert abs(a - b) <= 1e-4 * abs(b), (lg, le)
+    assert abs(lg[0] - le[0]) <= 1e-6 * abs(le[0]), (lg, le)      # same kernels, same order
+    for a, b in zip(lg, le):                            # capturable vs plain Adam differ in the last bits, and Adam
+        assert abs(a - b) <= 1e-2 * abs(b), (lg, le)    # turns them into +-lr steps on noise-level gradients
     assert abs(lg[0] - lo[0]) <= 1e-4 * abs(lo[0])
     for a, b in zip(lg, lo):                            # later iterations: Adam amplifies rounding, track loosely
         assert abs(a - b) <= 5e-2 * abs(b), (lg, lo)
