@@ -174,6 +174,17 @@ rowblock_kernel(const float* __restrict__ gX, const float* __restrict__ Y, const
     }
 }
 
+// dst[i,:] = src[idx[i],:]  (halo packing for the partitioned mode; one float4 per thread)
+__global__ void gather_rows_kernel(const float* __restrict__ src, const int* __restrict__ idx, float* __restrict__ dst,
+                                   int64_t m, int C4) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m * C4) return;
+    const int64_t r = i / C4;
+    const int c = (int)(i % C4);
+    const int64_t s = __ldg(idx + r);
+    reinterpret_cast<float4*>(dst)[i] = __ldg(reinterpret_cast<const float4*>(src) + s * C4 + c);
+}
+
 template <int MODE>
 static int launch_rowblock(const float* gX, const float* Y, const float* mean, const float* rstd, const float* scale,
                            const float* shift, float slope, const float* c1, const float* c2, float* dY,
@@ -233,6 +244,15 @@ int ddmp_bn_bwd_apply(const float* gX, const float* Y, const float* mean, const 
     if (n == 0) return DDMP_OK;
     return launch_rowblock<1>(gX, Y, mean, rstd, scale, shift, slope, c1, c2, dY, colsum_partials, n, C,
                               as_stream(stream), "bn_bwd_apply");
+}
+
+int ddmp_gather_rows(const float* src, const int32_t* idx, float* dst, int64_t m, int32_t C, void* stream) {
+    using namespace ddmp;
+    DDMP_REQUIRE(src && idx && dst && m >= 0 && C > 0 && C % 4 == 0, "gather_rows: bad arguments (C must be a multiple of 4)");
+    if (m == 0) return DDMP_OK;
+    const int64_t total = m * (C / 4);
+    gather_rows_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, as_stream(stream)>>>(src, idx, dst, m, C / 4);
+    return check_launch("gather_rows");
 }
 
 int ddmp_colsum_partials(const float* X, float* partials, int64_t n, int32_t C, void* stream) {

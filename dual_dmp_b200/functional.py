@@ -31,10 +31,13 @@ def num_row_blocks(n: int, C: int) -> int:
     return int(lib.query("ddmp_num_row_blocks", n, C))
 
 
-def spmm_gcn(graph: GcnGraph, H, bias=None, stats=False, transposed=False, out=None):
+def spmm_gcn(graph: GcnGraph, H, bias=None, stats=False, transposed=False, out=None, n_rows=None):
+    """n_rows < H.shape[0] in the partitioned mode: H = [owned | halo] rows, only the owned rows are computed"""
     n, C = H.shape
+    if n_rows is not None:
+        n = n_rows
     rowptr, col, w = (graph.rowptr_t, graph.col_t, graph.w_t) if transposed else (graph.rowptr, graph.col, graph.w)
-    Y = out if out is not None else torch.empty_like(H)
+    Y = out if out is not None else torch.empty(n, C, dtype=torch.float32, device=H.device)
     partials = torch.empty(num_row_blocks(n, C), 2, C, dtype=torch.float32, device=H.device) if stats else None
     lib.call("ddmp_spmm_gcn", ptr(rowptr), ptr(col), ptr(w), ptr(H), ptr(bias), ptr(Y), ptr(partials), n, C,
              stream_ptr(H.device))
@@ -82,6 +85,14 @@ def gemm_dw(dH, X, Cin, row_map=None, scale=None, shift=None, backend=None):
     return dW
 
 
+def partials_to_sums(partials):
+    """[nblk, sets, C] row-block partials -> [sets, C] (fixed order, float64 accumulate)"""
+    nblk, sets, C = partials.shape
+    out = torch.empty(sets, C, dtype=torch.float32, device=partials.device)
+    lib.call("ddmp_colsum_finalize", ptr(partials), nblk, sets, C, ptr(out), stream_ptr(partials.device))
+    return out
+
+
 def colsum(X):
     n, C = X.shape
     nblk = num_row_blocks(n, C)
@@ -102,8 +113,10 @@ def bn_stats_finalize(partials, n, gamma, beta, running_mean=None, running_var=N
     return stats
 
 
-def bn_lrelu_backward(gX, Y, stats, dY_out=None):
-    """gX = dL/d lrelu(bn(Y))  ->  (dY, dgamma, dbeta, dbias)."""
+def bn_lrelu_backward(gX, Y, stats, dY_out=None, comm=None):
+    """gX = dL/d lrelu(bn(Y))  ->  (dY, dgamma, dbeta, dbias).  ``comm`` (partitioned mode): the two column sums
+    are all-reduced over the ranks before they are used; dbias stays a per-rank partial (all-reduced with the
+    weight gradients)."""
     n, C = Y.shape
     dev = Y.device
     st = stream_ptr(dev)
@@ -113,8 +126,13 @@ def bn_lrelu_backward(gX, Y, stats, dY_out=None):
     mean, rstd, scale, shift = stats[0], stats[1], stats[2], stats[3]
     lib.call("ddmp_bn_bwd_reduce", ptr(gX), ptr(Y), ptr(mean), ptr(rstd), ptr(scale), ptr(shift), SLOPE,
              ptr(partials), n, C, st)
-    lib.call("ddmp_bn_bwd_finalize", ptr(partials), nblk, n, C, ptr(small[0]), ptr(small[1]), ptr(small[2]),
-             ptr(small[3]), st)
+    if comm is None:
+        lib.call("ddmp_bn_bwd_finalize", ptr(partials), nblk, n, C, ptr(small[0]), ptr(small[1]), ptr(small[2]),
+                 ptr(small[3]), st)
+    else:
+        sums = comm.allreduce_(partials_to_sums(partials))
+        lib.call("ddmp_bn_bwd_finalize", ptr(sums), 1, comm.n_global, C, ptr(small[0]), ptr(small[1]), ptr(small[2]),
+                 ptr(small[3]), st)
     dY = dY_out if dY_out is not None else torch.empty_like(Y)
     lib.call("ddmp_bn_bwd_apply", ptr(gX), ptr(Y), ptr(mean), ptr(rstd), ptr(scale), ptr(shift), SLOPE,
              ptr(small[2]), ptr(small[3]), ptr(dY), ptr(partials), n, C, st)
@@ -176,21 +194,29 @@ class GcnNetFunction(torch.autograd.Function):
         if x_in.shape != (n, Ws[0].shape[1]):
             raise RuntimeError(f"net input has shape {tuple(x_in.shape)}, expected {(n, Ws[0].shape[1])}")
         cmax = max(w.shape[0] for w in Ws)
-        Hbuf = torch.empty(n * cmax, dtype=torch.float32, device=dev)
+        comm = graph if hasattr(graph, "exchange") else None        # partitioned mode (dual_dmp_b200.partition)
+        n_ext = graph.n_ext if comm is not None else n
+        Hbuf = torch.empty(n_ext * cmax, dtype=torch.float32, device=dev)
         Ys, stats = [], []
         for l in range(L):
             cout = Ws[l].shape[0]
-            H = Hbuf[: n * cout].view(n, cout)
+            H = Hbuf[: n_ext * cout].view(n_ext, cout)               # [owned | halo] rows
             if l == 0:
                 gemm_xw(x_in, Ws[0], row_map=graph.perm, out=H, n=n)
             else:
                 gemm_xw(Ys[l - 1], Ws[l], scale=stats[l - 1][2], shift=stats[l - 1][3], out=H)
+            if comm is not None:
+                comm.exchange(H)
             if training:
-                Y, partials = spmm_gcn(graph, H, bias=bs[l], stats=True)
+                Y, partials = spmm_gcn(graph, H, bias=bs[l], stats=True, n_rows=n)
                 rm, rv = bn_buffers[l]
-                st = bn_stats_finalize(partials, n, gammas[l], betas[l], rm, rv)
+                if comm is None:
+                    st = bn_stats_finalize(partials, n, gammas[l], betas[l], rm, rv)
+                else:
+                    sums = comm.allreduce_(partials_to_sums(partials))
+                    st = bn_stats_finalize(sums.view(1, 2, cout), comm.n_global, gammas[l], betas[l], rm, rv)
             else:
-                Y = spmm_gcn(graph, H, bias=bs[l])
+                Y = spmm_gcn(graph, H, bias=bs[l], n_rows=n)
                 rm, rv = bn_buffers[l]
                 rstd = torch.rsqrt(rv + BN_EPS)
                 scale = gammas[l] * rstd
@@ -230,8 +256,10 @@ class GcnNetFunction(torch.autograd.Function):
         # ---- head ----
         go = torch.empty(n, 4, dtype=torch.float32, device=dev)
         gh = torch.empty(n, 16, dtype=torch.float32, device=dev)
+        comm = graph if hasattr(graph, "exchange") else None
+        n_ext = graph.n_ext if comm is not None else n
         bufA = torch.empty(n * cmax, dtype=torch.float32, device=dev)      # gX (grad wrt activated layer output)
-        bufB = torch.empty(n * cmax, dtype=torch.float32, device=dev)      # dY
+        bufB = torch.empty(n_ext * cmax, dtype=torch.float32, device=dev)  # dY  ([owned | halo] rows)
         bufC = torch.empty(n * cmax, dtype=torch.float32, device=dev)      # dH
         gX = bufA[: n * 32].view(n, 32)
         lib.call("ddmp_head_bwd", kind, ptr(g_out), ptr(graph.perm), ptr(W1), ptr(W2), ptr(ctx.h_save),
@@ -245,10 +273,12 @@ class GcnNetFunction(torch.autograd.Function):
         grads = [None] * (4 * L)
         for l in range(L - 1, -1, -1):
             cout, cin = Ws[l].shape
-            dY = bufB[: n * cout].view(n, cout)
-            _, dgamma, dbeta, dbias = bn_lrelu_backward(gX, Ys[l], stats[l], dY_out=dY)
+            dY = bufB[: n_ext * cout].view(n_ext, cout)
+            _, dgamma, dbeta, dbias = bn_lrelu_backward(gX, Ys[l], stats[l], dY_out=dY, comm=comm)
+            if comm is not None:
+                comm.exchange(dY)                   # A_hat symmetric: the backward needs dY of the halo rows
             dH = bufC[: n * cout].view(n, cout)
-            spmm_gcn(graph, dY, transposed=True, out=dH)
+            spmm_gcn(graph, dY, transposed=True, out=dH, n_rows=n)
             if l == 0:
                 gW = gemm_dw(dH, x_in, cin, row_map=graph.perm)
             else:
@@ -258,7 +288,18 @@ class GcnNetFunction(torch.autograd.Function):
             grads[4 * l: 4 * l + 4] = [gW, dbias, dgamma, dbeta]
         g_xpos = g_out if (kind == HEAD_POS and ctx.needs_input_grad[6]) else None
         ctx.Ys = ctx.stats = ctx.h_save = ctx.t_save = None
-        return (None, None, None, None, None, None, g_xpos, *grads, gW_lin1, gb_lin1, gW_lin2, gb_lin2)
+        all_grads = [*grads, gW_lin1, gb_lin1, gW_lin2, gb_lin2]
+        if comm is not None:
+            # weight / bias gradients are sums over rows: one all-reduce of the flattened per-rank partials
+            # (dgamma / dbeta were already reduced inside the layer loop and are identical on every rank)
+            idx = [i for i in range(len(all_grads)) if not (i < 4 * L and i % 4 in (2, 3))]
+            flat = comm.allreduce_(torch.cat([all_grads[i].reshape(-1) for i in idx]))
+            off = 0
+            for i in idx:
+                k = all_grads[i].numel()
+                all_grads[i] = flat[off: off + k].view_as(all_grads[i])
+                off += k
+        return (None, None, None, None, None, None, g_xpos, *all_grads)
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -89,6 +89,10 @@ int ddmp_colsum_finalize(const float* partials, int64_t nblk, int32_t sets, int3
 /* partials[b][0][c] = sum over row block b of X[:,c]  (bias gradients of the heads). */
 int ddmp_colsum_partials(const float* X, float* partials, int64_t n, int32_t C, void* stream);
 
+/* dst[i,:] = src[idx[i],:], C a multiple of 4: packs the boundary rows a peer rank needs before the NCCL exchange
+ * of the partitioned mode (SURVEY.md §8e mode B: per-layer halo exchange). */
+int ddmp_gather_rows(const float* src, const int32_t* idx, float* dst, int64_t m, int32_t C, void* stream);
+
 /* ---- dense feature transform ------------------------------------------------------------------------------ */
 /* H[n,Cout] = act(X)[n,Cin] * W[Cout,Cin]^T.   act(x)[i,k] = lrelu(scale[k]*X[r,k]+shift[k]) when scale != NULL
  * (the previous layer's BatchNorm+LeakyReLU applied on load), r = row_map[i] when row_map != NULL (first-layer

@@ -1,0 +1,91 @@
+"""Partitioned mode on real GPUs (needs >= 2 devices; run with `gpurun --gpus 2 -- python -m pytest
+tests/test_gpu_partition.py -m gpu`): one mesh split over 2 ranks with NCCL halo exchange + BatchNorm / weight
+gradient all-reduce must reproduce the single-GPU result (outputs, losses, every parameter gradient)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    import torch.distributed as dist
+    from tests.helpers import rel_err, small_case
+    from dual_dmp_b200.partition import PartitionedNet
+    from dual_dmp_b200.util import loss as L
+    from dual_dmp_b200.util.datamaker import dataset_from_meshes
+    from dual_dmp_b200.util.networks import NormalNet, PosNet
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    res = {}
+    try:
+        for kind, n in (("ico", 20), ("open", 14)):
+            n_mesh, s_mesh, _ = small_case(kind, n)
+            ds = dataset_from_meshes(n_mesh, s_mesh)
+            torch.manual_seed(0)
+            posnet, normnet = PosNet(dev).to(dev), NormalNet(dev).to(dev)
+            with torch.no_grad():
+                for net in (posnet, normnet):
+                    for i in range(1, 13):
+                        getattr(net, f"bn{i}").weight.uniform_(0.5, 1.5)
+                        getattr(net, f"bn{i}").bias.normal_(0, 0.2)
+
+            def run(pnet, nnet):
+                for net in (posnet, normnet):
+                    net.train(); net.zero_grad()
+                pos = pnet(ds)
+                nrm = nnet(ds)
+                ls = [L.pos_rec_loss(pos, n_mesh.vs), L.mesh_laplacian_loss(pos, n_mesh), L.norm_rec_loss(nrm, n_mesh.fn)]
+                l4, _ = L.fn_bnf_loss(pos, nrm, n_mesh, loop=2)
+                ls += [l4, L.pos_norm_loss(pos, nrm, n_mesh)]
+                (3.0 * ls[0] + 4.0 * ls[1] + 4.0 * ls[2] + 4.0 * ls[3] + 1.0 * ls[4]).backward()
+                grads = {("p." if net is posnet else "n.") + k: p.grad.detach().clone()
+                         for net in (posnet, normnet) for k, p in net.named_parameters()}
+                return pos.detach().clone(), nrm.detach().clone(), [float(x) for x in ls], grads
+
+            pos1, nrm1, l1, g1 = run(posnet, normnet)                                   # single GPU (replicated)
+            pos2, nrm2, l2, g2 = run(PartitionedNet(posnet, rank, world), PartitionedNet(normnet, rank, world))
+            worst = 0.0
+            for k in g1:
+                if ".conv" in k and k.endswith(".bias"):
+                    continue
+                worst = max(worst, rel_err(g2[k], g1[k]))
+            res[f"{kind}{n}"] = dict(pos=rel_err(pos2, pos1), nrm=rel_err(nrm2, nrm1),
+                                     loss=max(abs(a - b) / abs(b) for a, b in zip(l2, l1)), grad=worst)
+        q.put((rank, res, None))
+    except Exception as e:                                                              # noqa: BLE001
+        import traceback
+        q.put((rank, None, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_partitioned_matches_single_gpu():
+    from tests.helpers import report
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port, world = _free_port(), 2
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = sorted((q.get(timeout=600) for _ in range(world)), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=120)
+    for rank, res, err in out:
+        assert err is None, err
+        report(f"partitioned rank {rank}", res)
+        for case, r in res.items():
+            assert r["pos"] < 2e-5 and r["nrm"] < 2e-5 and r["loss"] < 1e-5 and r["grad"] < 1e-4, (rank, case, r)
