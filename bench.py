@@ -43,6 +43,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time the eager drop-in step instead of the CUDA-graph one")
+    ap.add_argument("--mode", default="independent", choices=["independent", "partition"],
+                    help="N>1: 'independent' = one mesh fit per GPU (weak scaling, default); 'partition' = ONE mesh "
+                         "range-partitioned over the GPUs with NCCL halo exchange (strong scaling)")
     ap.add_argument("--detail", default=None, help="write a per-kernel-group timing table (JSON) to this path")
     return ap.parse_args()
 
@@ -309,9 +312,89 @@ def run_reference(args):
     print(json.dumps(out), flush=True)
 
 
+def run_partitioned(args):
+    """mode B: one mesh over all ranks; value = iters/s of that ONE fit (strong scaling)"""
+    import torch.distributed as dist
+    from dual_dmp_b200 import dist as D
+    from dual_dmp_b200.partition import PartitionedNet
+    from dual_dmp_b200.util import loss as L
+    from dual_dmp_b200.util.networks import NormalNet, PosNet
+    rank, local_rank, world = D.env_rank_world()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_mesh, s_mesh, ds = build_case(args.n)
+    V, F = len(n_mesh.vs), len(n_mesh.faces)
+    torch.manual_seed(0)
+    posnet, normnet = PosNet(dev).to(dev), NormalNet(dev).to(dev)
+    if world > 1:
+        ppos, pnrm = PartitionedNet(posnet, rank, world), PartitionedNet(normnet, rank, world)
+    else:
+        ppos, pnrm = posnet, normnet
+        ds = ds.to(dev)
+    opt_pos = torch.optim.Adam(posnet.parameters(), lr=0.01)
+    opt_norm = torch.optim.Adam(normnet.parameters(), lr=0.01)
+    tgt_vs, tgt_fn = torch.from_numpy(n_mesh.vs).to(dev), torch.from_numpy(n_mesh.fn).to(dev)
+    k = args.k
+
+    def step(epoch):
+        posnet.train(); normnet.train()
+        opt_pos.zero_grad(); opt_norm.zero_grad()
+        pos = ppos(ds)
+        l1 = L.pos_rec_loss(pos, tgt_vs)
+        l2 = L.mesh_laplacian_loss(pos, n_mesh)
+        nrm = pnrm(ds)
+        l3 = L.norm_rec_loss(nrm, tgt_fn)
+        l4, _ = L.fn_bnf_loss(pos, nrm, n_mesh, loop=args.bnfloop)
+        if epoch <= 100:
+            l4 = l4 * 0.0
+        l5 = L.pos_norm_loss(pos, nrm, n_mesh)
+        loss = k[0] * l1 + k[1] * l2 + k[2] * l3 + k[3] * l4 + k[4] * l5
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(normnet.parameters(), 0.8)
+        opt_pos.step(); opt_norm.step()
+        return loss
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    for i in range(args.warmup):
+        step(101 + i)
+    D.barrier(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        loss = step(101 + args.warmup + i)
+    e1.record()
+    D.barrier(dev)
+    ms = D.max_over_ranks(e0.elapsed_time(e1), dev)
+    sampler.stop_flag = True
+    halo = {}
+    if world > 1:
+        for name, net in (("vertex_graph", posnet), ("face_graph", normnet)):
+            g = net.last_graph
+            halo[name] = {"owned_rows": g.n, "halo_rows": g.n_halo, "sent_rows": g.n_send}
+    mem = torch.cuda.max_memory_allocated(dev) / 2 ** 30
+    if rank == 0:
+        out = {"metric": METRIC, "value": 1000.0 * args.steps / ms, "unit": "iters/s", "n_gpus": world,
+               "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+               "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+               "config": {"workload": f"ONE synthetic icosphere n={args.n}: {F} faces / {V} vertices, Morton "
+                                      f"range-partitioned over {world} GPU(s), per-layer NCCL halo exchange, "
+                                      f"BatchNorm-statistic and weight-gradient all-reduce, replicated losses",
+                          "faces": F, "vertices": V, "mode": "partition", "rank0_partition": halo,
+                          "rank0_peak_mem_GiB": round(mem, 2)},
+               "e2e": None, "loss": float(loss), "clocks": sampler.summary()}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 if __name__ == "__main__":
     a = parse_args()
     if a.impl == "reference":
         run_reference(a)
+    elif a.mode == "partition":
+        run_partitioned(a)
     else:
         run_ours(a)

@@ -53,17 +53,39 @@ def _worker(rank, world, port, q):
                 (3.0 * ls[0] + 4.0 * ls[1] + 4.0 * ls[2] + 4.0 * ls[3] + 1.0 * ls[4]).backward()
                 grads = {("p." if net is posnet else "n.") + k: p.grad.detach().clone()
                          for net in (posnet, normnet) for k, p in net.named_parameters()}
-                return pos.detach().clone(), nrm.detach().clone(), [float(x) for x in ls], grads
+                return pos.detach().clone(), nrm.detach().clone(), [float(x.detach()) for x in ls], grads
 
+            def masks(net):      # LeakyReLU active sets of the 12 layers (+ head), rows in this run's own order
+                return [((y.double() * st[2].double() + st[3].double()) > 0) if st is not None else (y > 0)
+                        for y, st in net.taps]
+
+            posnet.taps, normnet.taps = [], []
             pos1, nrm1, l1, g1 = run(posnet, normnet)                                   # single GPU (replicated)
-            pos2, nrm2, l2, g2 = run(PartitionedNet(posnet, rank, world), PartitionedNet(normnet, rank, world))
+            m1 = {"p": masks(posnet), "n": masks(normnet)}
+            posnet.taps, normnet.taps = [], []
+            ppos, pnrm = PartitionedNet(posnet, rank, world), PartitionedNet(normnet, rank, world)
+            pos2, nrm2, l2, g2 = run(ppos, pnrm)
+            m2 = {"p": masks(posnet), "n": masks(normnet)}
+            # both runs use the same Morton order; this rank owns the contiguous rows [lo, hi) of it
+            flips = 0
+            for key, net in (("p", posnet), ("n", normnet)):
+                lo, hi = net.last_graph.lo, net.last_graph.hi
+                flips += sum(int((a[lo:hi] != b).sum()) for a, b in zip(m1[key], m2[key]))
+            fl = torch.tensor([flips], device=dev)
+            dist.all_reduce(fl)
             worst = 0.0
             for k in g1:
                 if ".conv" in k and k.endswith(".bias"):
                     continue
                 worst = max(worst, rel_err(g2[k], g1[k]))
+            # replicas must stay bitwise identical: compare this rank's gradients with rank 0's
+            flat = torch.cat([g2[k].reshape(-1) for k in sorted(g2)])
+            ref0 = flat.clone()
+            dist.broadcast(ref0, src=0)
             res[f"{kind}{n}"] = dict(pos=rel_err(pos2, pos1), nrm=rel_err(nrm2, nrm1),
-                                     loss=max(abs(a - b) / abs(b) for a, b in zip(l2, l1)), grad=worst)
+                                     loss=max(abs(a - b) / abs(b) for a, b in zip(l2, l1)), grad=worst,
+                                     flips=int(fl.item()), replicas_identical=bool(torch.equal(flat, ref0)))
+            posnet.taps = normnet.taps = None
         q.put((rank, res, None))
     except Exception as e:                                                              # noqa: BLE001
         import traceback
@@ -88,4 +110,8 @@ def test_partitioned_matches_single_gpu():
         assert err is None, err
         report(f"partitioned rank {rank}", res)
         for case, r in res.items():
-            assert r["pos"] < 2e-5 and r["nrm"] < 2e-5 and r["loss"] < 1e-5 and r["grad"] < 1e-4, (rank, case, r)
+            assert r["pos"] < 2e-5 and r["nrm"] < 2e-5 and r["loss"] < 1e-5 and r["replicas_identical"], (rank, case, r)
+            # a LeakyReLU pre-activation within rounding of zero may take the other branch when the BatchNorm sums
+            # are combined in a different order (tests/helpers.MaskedLeaky explains the effect); without such a flip
+            # the gradients must agree to rounding
+            assert r["grad"] < (1e-4 if r["flips"] == 0 else 2e-2), (rank, case, r)
