@@ -36,7 +36,8 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=224, help="icosphere frequency: F = 20 n^2 (224 -> 1,003,520 faces)")
+    ap.add_argument("--n", "--freq", dest="n", type=int, default=224,
+                    help="icosphere frequency: F = 20 n^2 (224 -> 1,003,520 faces); use --freq under torchrun")
     ap.add_argument("--bnfloop", type=int, default=1)
     ap.add_argument("--k", type=float, nargs=5, default=[3.0, 4.0, 4.0, 4.0, 1.0])
     ap.add_argument("--cpu-n", type=int, default=40, help="icosphere frequency of the bounded CPU-baseline sample")
