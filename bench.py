@@ -56,9 +56,10 @@ def build_case(n):
     from dual_dmp_b200 import synth
     from dual_dmp_b200.util.datamaker import dataset_from_meshes
     from dual_dmp_b200.util.mesh import Mesh
+    from types import SimpleNamespace
     case = synth.make_case(n)
     n_mesh = Mesh(vs=case.noise_vs, faces=case.faces)
-    s_mesh = Mesh(vs=case.smooth_vs, faces=case.faces)
+    s_mesh = SimpleNamespace(vs=case.smooth_vs)      # only the smoothed vertices are read (reference datamaker.py:87)
     return n_mesh, s_mesh, dataset_from_meshes(n_mesh, s_mesh)
 
 
