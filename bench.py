@@ -43,6 +43,7 @@ def parse_args():
     ap.add_argument("--cpu-n", type=int, default=40, help="icosphere frequency of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="run PosNet and NormalNet on one stream")
     ap.add_argument("--no-graph", action="store_true", help="time the eager drop-in step instead of the CUDA-graph one")
     ap.add_argument("--mode", default="independent", choices=["independent", "partition"],
                     help="N>1: 'independent' = one mesh fit per GPU (weak scaling, default); 'partition' = ONE mesh "
@@ -170,7 +171,8 @@ def run_ours(args):
     # replayed as a CUDA graph.  --no-graph times the eager drop-in step instead.
     import copy
     from dual_dmp_b200.step import DualStep
-    stepper = DualStep(posnet, normnet, ds, n_mesh, k=k, bnfloop=args.bnfloop, capture=not args.no_graph)
+    stepper = DualStep(posnet, normnet, ds, n_mesh, k=k, bnfloop=args.bnfloop, capture=not args.no_graph,
+                       overlap=not args.no_overlap)
     ds_dev, tgt_vs, tgt_fn = stepper.dataset, stepper.tgt_vs, stepper.tgt_fn
     opt_pos, opt_norm = stepper.opt_pos, stepper.opt_norm
     epoch0 = 101   # past the reference's 100-iteration BNF warm-up, so every loss term is live

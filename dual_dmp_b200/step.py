@@ -20,7 +20,7 @@ from .util import loss as L
 
 class DualStep:
     def __init__(self, posnet, normnet, dataset, n_mesh, k=(3.0, 4.0, 4.0, 4.0, 1.0), bnfloop=1, pos_lr=0.01,
-                 norm_lr=0.01, grad_clip=0.8, bnf_warmup_epochs=100, capture=True):
+                 norm_lr=0.01, grad_clip=0.8, bnf_warmup_epochs=100, capture=True, overlap=True):
         dev = torch.device(posnet.device)
         if dev.type != "cuda":
             raise RuntimeError("DualStep runs on CUDA only (dual_dmp_b200 has no CPU path)")
@@ -32,6 +32,11 @@ class DualStep:
         self.tgt_vs = torch.from_numpy(n_mesh.vs).to(dev)               # float64 targets, like the reference
         self.tgt_fn = torch.from_numpy(n_mesh.fn).to(dev)
         self.capture = bool(capture)
+        # PosNet and NormalNet are independent until the losses: run them on two streams so the memory-bound
+        # kernels of one network (SpMM, BatchNorm) overlap the tensor-core GEMMs of the other; autograd runs each
+        # network's backward on the stream of its forward
+        self.overlap = bool(overlap)
+        self._streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev)) if self.overlap else None
         self.opt_pos = torch.optim.Adam(posnet.parameters(), lr=pos_lr, capturable=self.capture)
         self.opt_norm = torch.optim.Adam(normnet.parameters(), lr=norm_lr, capturable=self.capture)
         self._graphs: dict = {}
@@ -47,10 +52,24 @@ class DualStep:
         self.normnet.train()
         self.opt_pos.zero_grad(set_to_none=True)
         self.opt_norm.zero_grad(set_to_none=True)
-        pos = self.posnet(self.dataset)
+        if self.overlap:
+            cur = torch.cuda.current_stream(self.device)
+            s_pos, s_nrm = self._streams
+            s_pos.wait_stream(cur)
+            s_nrm.wait_stream(cur)
+            with torch.cuda.stream(s_nrm):           # the larger network first
+                nrm = self.normnet(self.dataset)
+            with torch.cuda.stream(s_pos):
+                pos = self.posnet(self.dataset)
+            cur.wait_stream(s_pos)
+            cur.wait_stream(s_nrm)
+            pos.record_stream(cur)
+            nrm.record_stream(cur)
+        else:
+            pos = self.posnet(self.dataset)
+            nrm = self.normnet(self.dataset)
         l1 = L.pos_rec_loss(pos, self.tgt_vs)
         l2 = L.mesh_laplacian_loss(pos, self.mesh)
-        nrm = self.normnet(self.dataset)
         l3 = L.norm_rec_loss(nrm, self.tgt_fn)
         l4, _ = L.fn_bnf_loss(pos, nrm, self.mesh, loop=self.bnfloop)
         if bnf_off:
