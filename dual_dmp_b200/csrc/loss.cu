@@ -436,9 +436,17 @@ grad_norm_kernel(const float* __restrict__ g, float* norm_out, LossScratch* sc, 
     if (finish_sum(acc, sc, tot)) *norm_out = (float)sqrt(tot);
 }
 
+__global__ void counter_increment_kernel(int64_t* counter) { *counter += 1; }
+
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, const float* __restrict__ clip_norm, float max_norm, float lr,
-                            float beta1, float beta2, float eps, float bc1, float bc2_sqrt, int64_t count) {
+                            float beta1, float beta2, float eps, float bc1, float bc2_sqrt,
+                            const int64_t* __restrict__ step_dev, int64_t count) {
+    if (step_dev) {   // step count lives on the device (CUDA-graph replay: kernel arguments are frozen)
+        const double t = (double)*step_dev;
+        bc1 = (float)(1.0 - pow((double)beta1, t));
+        bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, t));
+    }
     float coef = 1.f;
     if (clip_norm) {
         coef = max_norm / (*clip_norm + 1.0e-6f);
@@ -653,8 +661,21 @@ int ddmp_adam_step(float* param, const float* grad, float* exp_avg, float* exp_a
     const double bc1 = 1.0 - pow((double)beta1, (double)step);
     const double bc2 = 1.0 - pow((double)beta2, (double)step);
     LAUNCH_1D(adam_kernel, count, as_stream(stream), param, grad, exp_avg, exp_avg_sq, clip_norm, max_norm, lr,
-              beta1, beta2, eps, (float)bc1, (float)sqrt(bc2), count);
+              beta1, beta2, eps, (float)bc1, (float)sqrt(bc2), (const int64_t*)nullptr, count);
     return check_launch("adam_step");
+}
+
+int ddmp_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, const float* clip_norm,
+                       float max_norm, float lr, float beta1, float beta2, float eps, int64_t* step_counter,
+                       int64_t count, void* stream) {
+    using namespace ddmp;
+    DDMP_REQUIRE(param && grad && exp_avg && exp_avg_sq && step_counter && count > 0, "adam_step_dev: bad arguments");
+    counter_increment_kernel<<<1, 1, 0, as_stream(stream)>>>(step_counter);
+    int rc = check_launch("adam_step_dev(counter)");
+    if (rc) return rc;
+    LAUNCH_1D(adam_kernel, count, as_stream(stream), param, grad, exp_avg, exp_avg_sq, clip_norm, max_norm, lr,
+              beta1, beta2, eps, 1.f, 1.f, (const int64_t*)step_counter, count);
+    return check_launch("adam_step_dev");
 }
 
 }  // extern "C"

@@ -20,7 +20,8 @@ from .util import loss as L
 
 class DualStep:
     def __init__(self, posnet, normnet, dataset, n_mesh, k=(3.0, 4.0, 4.0, 4.0, 1.0), bnfloop=1, pos_lr=0.01,
-                 norm_lr=0.01, grad_clip=0.8, bnf_warmup_epochs=100, capture=True, overlap=True):
+                 norm_lr=0.01, grad_clip=0.8, bnf_warmup_epochs=100, capture=True, overlap=True,
+                 fused_optimizer=True):
         dev = torch.device(posnet.device)
         if dev.type != "cuda":
             raise RuntimeError("DualStep runs on CUDA only (dual_dmp_b200 has no CPU path)")
@@ -37,8 +38,13 @@ class DualStep:
         # network's backward on the stream of its forward
         self.overlap = bool(overlap)
         self._streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev)) if self.overlap else None
-        self.opt_pos = torch.optim.Adam(posnet.parameters(), lr=pos_lr, capturable=self.capture)
-        self.opt_norm = torch.optim.Adam(normnet.parameters(), lr=norm_lr, capturable=self.capture)
+        self.fused_optimizer = bool(fused_optimizer)
+        if self.fused_optimizer:       # clip + Adam as two library kernels per network over flat buffers
+            self.opt_pos = FusedAdam(posnet, lr=pos_lr)
+            self.opt_norm = FusedAdam(normnet, lr=norm_lr, max_norm=self.grad_clip)
+        else:
+            self.opt_pos = torch.optim.Adam(posnet.parameters(), lr=pos_lr, capturable=self.capture)
+            self.opt_norm = torch.optim.Adam(normnet.parameters(), lr=norm_lr, capturable=self.capture)
         self._graphs: dict = {}
         self._static_loss: dict = {}
         self._eager_calls = 0
@@ -77,7 +83,8 @@ class DualStep:
         l5 = L.pos_norm_loss(pos, nrm, self.mesh)
         loss = k[0] * l1 + k[1] * l2 + k[2] * l3 + k[3] * l4 + k[4] * l5
         loss.backward()
-        torch.nn.utils.clip_grad_norm_(self.normnet.parameters(), self.grad_clip)
+        if not self.fused_optimizer:
+            torch.nn.utils.clip_grad_norm_(self.normnet.parameters(), self.grad_clip)
         self.opt_pos.step()
         self.opt_norm.step()
         self.pos, self.norm = pos.detach(), nrm.detach()
@@ -108,3 +115,49 @@ class DualStep:
             self._capture(bnf_off)
         self._graphs[bnf_off].replay()
         return self._static_loss[bnf_off]
+
+
+class FusedAdam:
+    """``clip_grad_norm_`` + ``torch.optim.Adam`` of one network as two library kernels over flat buffers
+    (reference main.py:108-110).  The parameters of ``module`` are re-pointed at views of one flat
+    buffer, so ``module.parameters()`` / ``state_dict()`` keep working; the step count lives on the device, which
+    makes ``step()`` CUDA-graph capturable."""
+
+    def __init__(self, module, lr=0.01, betas=(0.9, 0.999), eps=1e-8, max_norm=None):
+        from ._lib import lib
+        self.params = [p for p in module.parameters() if p.requires_grad]
+        dev = self.params[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("FusedAdam runs on CUDA only (dual_dmp_b200 has no CPU path)")
+        n = sum(p.numel() for p in self.params)
+        self.flat = torch.empty(n, dtype=torch.float32, device=dev)
+        off = 0
+        for p in self.params:
+            k = p.numel()
+            self.flat[off: off + k].copy_(p.detach().reshape(-1))
+            p.data = self.flat[off: off + k].view_as(p)
+            off += k
+        self.exp_avg = torch.zeros_like(self.flat)
+        self.exp_avg_sq = torch.zeros_like(self.flat)
+        self.step_count = torch.zeros((), dtype=torch.int64, device=dev)
+        self.norm = torch.zeros((), dtype=torch.float32, device=dev)
+        self.scratch = torch.zeros(lib.query("ddmp_loss_scratch_bytes") // 8 + 1, dtype=torch.float64, device=dev)
+        self.lr, self.betas, self.eps, self.max_norm = float(lr), betas, float(eps), max_norm
+        self.device = dev
+
+    def zero_grad(self, set_to_none=True):
+        for p in self.params:
+            p.grad = None
+
+    def step(self):
+        from ._lib import lib, ptr, set_device, stream_ptr
+        set_device(self.device)
+        st = stream_ptr(self.device)
+        g = torch.cat([p.grad.reshape(-1) for p in self.params])        # flat gradient (one gather kernel)
+        clip = None
+        if self.max_norm is not None:
+            lib.call("ddmp_grad_norm", ptr(g), ptr(self.norm), ptr(self.scratch), g.numel(), st)
+            clip = self.norm
+        lib.call("ddmp_adam_step_dev", ptr(self.flat), ptr(g), ptr(self.exp_avg), ptr(self.exp_avg_sq), ptr(clip),
+                 float(self.max_norm or 0.0), self.lr, self.betas[0], self.betas[1], self.eps, ptr(self.step_count),
+                 g.numel(), st)

@@ -203,6 +203,12 @@ int ddmp_adam_step(float* param, const float* grad, float* exp_avg, float* exp_a
                    float max_norm, float lr, float beta1, float beta2, float eps, int64_t step, int64_t count,
                    void* stream);
 
+/* Same update with the step count kept in device memory (incremented by the call): what a CUDA-graph-replayed
+ * iteration needs, since kernel arguments are frozen at capture. */
+int ddmp_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, const float* clip_norm,
+                       float max_norm, float lr, float beta1, float beta2, float eps, int64_t* step_counter,
+                       int64_t count, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -299,3 +299,25 @@ def test_gemm_tcgen05_3xtf32(cin, cout, n):
     assert torch.equal(a, b)
     # and it agrees with the FFMA kernel to fp32 rounding
     assert rel_err(a, F_.gemm_xw(Xn, Wd, scale=sc, shift=sh, backend=1)) < 1e-5
+
+
+def test_fused_clip_adam_matches_torch():
+    """ddmp_grad_norm + ddmp_adam_step_dev over flat buffers == clip_grad_norm_ + torch.optim.Adam (main.py:108-110)"""
+    from dual_dmp_b200.step import FusedAdam
+    torch.manual_seed(0)
+    shapes = [(32, 7), (32,), (512, 256), (512,), (3, 16), (3,)]
+    ref = torch.nn.ParameterList([torch.nn.Parameter(torch.randn(*s, device=DEV)) for s in shapes])
+    mine = torch.nn.ParameterList([torch.nn.Parameter(p.detach().clone()) for p in ref])
+    opt_ref = torch.optim.Adam(ref.parameters(), lr=0.01)
+    opt = FusedAdam(mine, lr=0.01, max_norm=0.8)
+    for it in range(5):
+        grads = [torch.randn(*s, device=DEV) * (10.0 if it % 2 == 0 else 0.01) for s in shapes]   # clipped / not
+        for p, q, g in zip(ref, mine, grads):
+            p.grad, q.grad = g.clone(), g.clone()
+        torch.nn.utils.clip_grad_norm_(ref.parameters(), 0.8)
+        opt_ref.step()
+        opt.step()
+        for p, q in zip(ref, mine):
+            assert rel_err(q, p) < 2e-6, (it, rel_err(q, p))
+    assert int(opt.step_count) == 5
+    assert all(q.data_ptr() >= opt.flat.data_ptr() for q in mine)         # parameters are views of the flat buffer
