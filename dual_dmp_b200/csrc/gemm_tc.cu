@@ -350,6 +350,8 @@ struct Nt2Args {
     int N, K;
     int tiles_n;
     int64_t num_tiles;
+    int knockout;         // profiling only (DDMP_TC_KNOCKOUT): 1 = no A loads, 2 = no A loads/stores, 4 = no C stores,
+                          // 8 = no B bulk copies (results are garbage; timing only)
 };
 
 // W [N,K] (or, transposed, W^T given as [K,N]) -> image; one thread per (n, 16-byte chunk of K)
@@ -402,6 +404,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) tc_gemm_nt2_kernel(const Nt2Arg
     uint64_t* acc_full = empty_bar + STAGES;     // [2]
     uint64_t* acc_empty = acc_full + 2;          // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    uint8_t* staging = smem + STAGES * STAGE_BYTES + 256;   // 4 epilogue warps x 32 rows x 128 B
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_kb = g.K / BK;
@@ -448,13 +451,15 @@ __global__ void __launch_bounds__(kV2Threads, 1) tc_gemm_nt2_kernel(const Nt2Arg
                     float4 av[NJ];
 #pragma unroll
                     for (int j = 0; j < NJ; ++j)
-                        av[j] = (src_row[j] >= 0) ? ldg4(g.A + src_row[j] * g.K + k0) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        av[j] = (src_row[j] >= 0 && !(g.knockout & 3)) ? ldg4(g.A + src_row[j] * g.K + k0)
+                                                                       : make_float4(1.f, 2.f, 3.f, 4.f);
                     float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (has_act) { sc = ldg4(g.scale + k0); sh = ldg4(g.shift + k0); }
                     mbar_wait(empty_bar + s, ph ^ 1u);
                     const uint32_t st = smem_base + s * STAGE_BYTES;
 #pragma unroll
                     for (int j = 0; j < NJ; ++j) {
+                        if (g.knockout & 2) break;
                         const uint32_t row = (t / CPR) + j * RPP;
                         float4 a = av[j];
                         if (has_act && src_row[j] >= 0) {
@@ -585,6 +590,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) tc_gemm_nt2_kernel(const Nt2Arg
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
                     mbar_wait(empty_bar + s, ph ^ 1u);
+                    if (g.knockout & 8) { mbar_arrive(full_bar + s); continue; }
                     mbar_arrive_expect_tx(full_bar + s, 2 * B_BYTES);
                     bulk_g2s(smem_base + s * STAGE_BYTES + 2 * A_BYTES, src + (int64_t)kb * (2 * (int64_t)B_BYTES),
                              2 * B_BYTES, full_bar + s);
@@ -593,12 +599,15 @@ __global__ void __launch_bounds__(kV2Threads, 1) tc_gemm_nt2_kernel(const Nt2Arg
         }
         __syncwarp();
     } else if (warp >= 12) {
-        // ===== epilogue: TMEM -> registers -> global, overlapped with the next tile's main loop =====
+        // ===== epilogue: TMEM -> registers -> (smem transpose) -> global, overlapped with the next tile's main loop =====
+        // tcgen05.ld hands every thread one ROW (32 columns); writing that straight out makes each warp store touch 32
+        // rows x 16 B.  A 16-KB swizzled staging tile per warp turns it into 4 rows x 128 B per store instruction.
         const int q = warp & 3;
+        const uint32_t stg = smem_u32(staging) + (uint32_t)q * (32u * 128u);
         uint32_t tile_no = 0;
         for (int64_t tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++tile_no) {
             const uint32_t buf = tile_no & 1u;
-            const int64_t m = (tile / g.tiles_n) * BM + q * 32 + lane;
+            const int64_t mrow0 = (tile / g.tiles_n) * BM + q * 32;
             const int n0 = (int)(tile % g.tiles_n) * BN;
             mbar_wait(acc_full + buf, (tile_no >> 1) & 1u);
             tc_fence_after();
@@ -606,13 +615,23 @@ __global__ void __launch_bounds__(kV2Threads, 1) tc_gemm_nt2_kernel(const Nt2Arg
             for (int cb = 0; cb < BN; cb += 32) {
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)cb, v);
-                if (m < g.M) {
-                    float* dst = g.C + m * g.N + n0 + cb;
 #pragma unroll
-                    for (int e = 0; e < 32; e += 4)
-                        st4(dst + e, make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]),
-                                                 __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3])));
+                for (int i = 0; i < 8; ++i)          // row = lane, 16-byte chunk i -> swizzled chunk i ^ (lane & 7)
+                    sts128(stg + (uint32_t)lane * 128u + (uint32_t)((i ^ (lane & 7)) << 4),
+                           make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int r = j * 4 + (lane >> 3), cc = lane & 7;
+                    uint4 o;
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w)
+                                 : "r"(stg + (uint32_t)r * 128u + (uint32_t)((cc ^ (r & 7)) << 4)));
+                    const int64_t m = mrow0 + r;
+                    if (m < g.M && !(g.knockout & 4))
+                        *reinterpret_cast<uint4*>(g.C + m * g.N + n0 + cb + cc * 4) = o;
                 }
+                __syncwarp();
             }
             tc_fence_before();
             __syncwarp();
@@ -628,7 +647,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) tc_gemm_nt2_kernel(const Nt2Arg
 
 template <int BN, int STAGES, bool DEEP, int KB>
 static int launch_nt2_impl(const Nt2Args& g, cudaStream_t st) {
-    constexpr size_t smem = (size_t)STAGES * (2 * BM * KB * 4 + 2 * BN * KB * 4) + 1024 + 256;
+    constexpr size_t smem = (size_t)STAGES * (2 * BM * KB * 4 + 2 * BN * KB * 4) + 1024 + 256 + 4 * 32 * 128;
     static bool configured = false;
     if (!configured) {
         DDMP_CUDA(cudaFuncSetAttribute(tc_gemm_nt2_kernel<BN, STAGES, DEEP, KB>,
@@ -670,6 +689,9 @@ static int run_nt2(const float* A, const int* a_map, const float* scale, const f
     g.M = M; g.N = N; g.K = K; g.tiles_n = N / BN;
     g.num_tiles = ceil_div(M, BM) * g.tiles_n;
     DDMP_REQUIRE(g.num_tiles < (1ll << 31), "tc gemm: too many tiles");
+    static const int knockout = [] { const char* e = getenv("DDMP_TC_KNOCKOUT"); return e ? atoi(e) : 0; }();
+    g.knockout = knockout;
+    if (knockout) { static bool said = false; if (!said) { fprintf(stderr, "[ddmp] tc knockout=%d\n", knockout); said = true; } }
     if (BN == 256) return launch_nt2<256, 2>(g, st);
     if (BN == 128) return launch_nt2<128, 3>(g, st);
     return launch_nt2<64, 4>(g, st);
