@@ -722,8 +722,9 @@ struct TnArgs {
     int64_t num_items;
 };
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(kThreads, 1) tc_gemm_tn_kernel(const TnArgs g) {
+template <int BN, int STAGES, int PW>
+__global__ void __launch_bounds__(PW * 32 + 32, 1) tc_gemm_tn_kernel(const TnArgs g) {
+    constexpr int kPT = PW * 32;                     // producer threads (PW warps) + one MMA warp
     constexpr uint32_t A_BYTES = BM * 128;           // 32 k-rows x 128 m x 4 B
     constexpr uint32_t B_BYTES = BN * 128;
     constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
@@ -742,14 +743,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_tn_kernel(const TnArgs g)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(full_bar + s, kProducerWarps);
+            mbar_init(full_bar + s, PW);
             mbar_init(empty_bar + s, 1);
         }
         mbar_init(accum_bar, 1);
-        mbar_init(drained_bar, kProducerWarps);
+        mbar_init(drained_bar, PW);
         fence_barrier_init();
     }
-    if (warp == kProducerWarps) tmem_alloc(tmem_slot, TMEM_COLS);
+    if (warp == PW) tmem_alloc(tmem_slot, TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -767,12 +768,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_tn_kernel(const TnArgs g)
         const int64_t r1 = (r0 + kSegRows < g.rows) ? (r0 + kSegRows) : g.rows;
         const int num_kb = (int)((r1 - r0 + BK - 1) / BK);
 
-        if (warp < kProducerWarps) {
+        if (warp < PW) {
             const int t = threadIdx.x;
             // A: 32 chunks per k-row (BM=128) -> 8 k-rows per pass of 256 threads; B: B_CH chunks per k-row
             const uint32_t a_cm = t % A_CH, a_r = t / A_CH;                    // a_r in [0, 256/A_CH)
             const uint32_t b_cm = t % B_CH, b_r = t / B_CH;
-            constexpr int A_PASS = kProducerThreads / A_CH, B_PASS = kProducerThreads / B_CH;
+            constexpr int A_PASS = kPT / A_CH, B_PASS = kPT / B_CH;
             const bool a_ok = (m0 + (int)a_cm * 4) < g.M;
             const bool has_act = g.scale != nullptr;
             float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -837,11 +838,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_tn_kernel(const TnArgs g)
             // ---- epilogue of this item ----
             mbar_wait(accum_bar, item_no & 1u);
             tc_fence_after();
-            const int q = warp & 3, half = warp >> 2;
+            constexpr int PARTS = PW / 4;                // warps sharing one TMEM lane quarter split the columns
+            constexpr int CPART = (BN / PARTS) < 32 ? 32 : (BN / PARTS);
+            const int q = warp & 3, part = warp >> 2;
             const int m = m0 + q * 32 + lane;
             float* prow = g.P + (seg * g.M + m) * (int64_t)g.N + n0;
 #pragma unroll 1
-            for (int cb = half * (BN / 2); cb < (half + 1) * (BN / 2); cb += 32) {
+            for (int cb = part * CPART; cb < (part + 1) * CPART && cb < BN; cb += 32) {
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, v);
                 if (m < g.M) {
@@ -888,7 +891,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_tn_kernel(const TnArgs g)
         }
     }
     __syncthreads();
-    if (warp == kProducerWarps) {
+    if (warp == PW) {
         tc_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);
     }
@@ -904,18 +907,26 @@ __global__ void seg_reduce_kernel(const float* __restrict__ partials, float* __r
     out[i] = (float)s;
 }
 
-template <int BN, int STAGES>
-static int launch_tn(const TnArgs& g, cudaStream_t st) {
+template <int BN, int STAGES, int PW>
+static int launch_tn_impl(const TnArgs& g, cudaStream_t st) {
     constexpr size_t smem = (size_t)STAGES * (2 * BM * 128 + 2 * BN * 128) + 1024 + 256;
     static bool configured = false;
     if (!configured) {
-        DDMP_CUDA(cudaFuncSetAttribute(tc_gemm_tn_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        DDMP_CUDA(cudaFuncSetAttribute(tc_gemm_tn_kernel<BN, STAGES, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
         configured = true;
     }
     const int64_t grid = g.num_items < kNumSMs ? g.num_items : kNumSMs;
-    tc_gemm_tn_kernel<BN, STAGES><<<(unsigned)grid, kThreads, smem, st>>>(g);
+    tc_gemm_tn_kernel<BN, STAGES, PW><<<(unsigned)grid, PW * 32 + 32, smem, st>>>(g);
     return check_launch("tc_gemm_tn");
+}
+// producer warps: both operands are split in flight here, so the transform is issue-bound with 8 warps (ncu: 42 %
+// issue utilisation, tensor pipe 45 %); DDMP_TC_TN_WARPS=8 restores the narrow version for A/B runs
+template <int BN, int STAGES>
+static int launch_tn(const TnArgs& g, cudaStream_t st) {
+    static const int pw = [] { const char* e = getenv("DDMP_TC_TN_WARPS"); return (e && atoi(e) == 8) ? 8 : 16; }();
+    if (pw == 16 && BN >= 128) return launch_tn_impl<BN, STAGES, 16>(g, st);
+    return launch_tn_impl<BN, STAGES, 8>(g, st);
 }
 
 __global__ void transpose_kernel(const float* __restrict__ W, float* __restrict__ Wt, int rows, int cols) {
