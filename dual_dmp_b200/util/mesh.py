@@ -54,21 +54,46 @@ class Mesh:
 
     # ---- OBJ ingest (reference util/mesh.py:23-43) -----------------------------------------------------
     def fill_from_file(self, path):
-        vs, faces = [], []
+        """Same grammar as the reference parser (``v x y z ...``, ``f a[/..] b[/..] c[/..]``, 1-based or negative
+        indices, everything else ignored).  The payloads of all ``v`` / ``f`` lines are converted by one C-level
+        ``np.fromstring`` each when the file is plain (exactly three numbers per ``v`` line, no ``/`` in ``f`` lines);
+        otherwise a per-line tokeniser handles extra columns and ``a/b/c`` references."""
         with open(path) as f:
-            for line in f:
-                sp = line.split()
-                if not sp:
-                    continue
-                if sp[0] == "v":
-                    vs.append((float(sp[1]), float(sp[2]), float(sp[3])))
-                elif sp[0] == "f":
-                    ids = [int(c.split("/")[0]) for c in sp[1:]]
-                    assert len(ids) == 3
-                    nv = len(vs)
-                    faces.append([(i - 1) if i >= 0 else (nv + i) for i in ids])
-        vs = np.asarray(vs, dtype=np.float64).reshape(-1, 3)
-        faces = np.asarray(faces, dtype=int).reshape(-1, 3)
+            lines = f.read().split("\n")
+        v_lines, f_lines, f_pos = [], [], []
+        for ln in lines:
+            if ln.startswith("v ") or ln.startswith("v\t"):
+                v_lines.append(ln[2:])
+            elif ln.startswith("f ") or ln.startswith("f\t"):
+                f_lines.append(ln[2:])
+                f_pos.append(len(v_lines))       # vertices defined so far (negative indices are relative to it)
+            elif ln[:1] in (" ", "\t"):          # indented keyword: take the slow, fully general route
+                sp = ln.split(None, 1)
+                if len(sp) == 2 and sp[0] == "v":
+                    v_lines.append(sp[1])
+                elif len(sp) == 2 and sp[0] == "f":
+                    f_lines.append(sp[1])
+                    f_pos.append(len(v_lines))
+        vs = np.zeros((0, 3), dtype=np.float64)
+        if v_lines:
+            flat = np.fromstring(" ".join(v_lines), dtype=np.float64, sep=" ")
+            if flat.size == 3 * len(v_lines):
+                vs = flat.reshape(-1, 3)
+            else:                                # extra columns (w, colours): keep the first three like the reference
+                vs = np.array([ln.split()[:3] for ln in v_lines]).astype(np.float64).reshape(-1, 3)
+        faces = np.zeros((0, 3), dtype=int)
+        if f_lines:
+            text = " ".join(f_lines)
+            if "/" not in text:
+                flat = np.fromstring(text, dtype=np.int64, sep=" ")
+                assert flat.size == 3 * len(f_lines)
+                flat = flat.reshape(-1, 3)
+            else:
+                toks = [ln.split() for ln in f_lines]
+                assert all(len(t) == 3 for t in toks)
+                flat = np.array([c.split("/", 1)[0] for t in toks for c in t]).astype(np.int64).reshape(-1, 3)
+            rel = np.asarray(f_pos, dtype=np.int64)[:, None]
+            faces = np.where(flat >= 0, flat - 1, rel + flat).astype(int)
         assert np.logical_and(faces >= 0, faces < len(vs)).all()
         return vs, faces
 
