@@ -24,6 +24,12 @@ import numpy as np
 import torch
 
 
+def _fromtext(text, dtype):
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", DeprecationWarning)     # text-mode fromstring: the C tokeniser is the point
+        return np.fromstring(text, dtype=dtype, sep=" ")
+
+
 def _coo(inds, vals, size):
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")          # "Sparse invariant checks are implicitly disabled"
@@ -76,7 +82,7 @@ class Mesh:
                     f_pos.append(len(v_lines))
         vs = np.zeros((0, 3), dtype=np.float64)
         if v_lines:
-            flat = np.fromstring(" ".join(v_lines), dtype=np.float64, sep=" ")
+            flat = _fromtext(" ".join(v_lines), np.float64)
             if flat.size == 3 * len(v_lines):
                 vs = flat.reshape(-1, 3)
             else:                                # extra columns (w, colours): keep the first three like the reference
@@ -85,7 +91,7 @@ class Mesh:
         if f_lines:
             text = " ".join(f_lines)
             if "/" not in text:
-                flat = np.fromstring(text, dtype=np.int64, sep=" ")
+                flat = _fromtext(text, np.int64)
                 assert flat.size == 3 * len(f_lines)
                 flat = flat.reshape(-1, 3)
             else:
