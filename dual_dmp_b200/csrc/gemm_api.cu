@@ -48,10 +48,10 @@ int ddmp_gemm_xw(const float* X, const int32_t* row_map, const float* scale, con
                  const float* W, float* H, void* workspace, int64_t workspace_bytes, int64_t n, int32_t Cin,
                  int32_t Cout, int backend, void* stream) {
     using namespace ddmp;
-    DDMP_REQUIRE(X && W && H, "gemm_xw: null pointer");
-    DDMP_REQUIRE((scale == nullptr) == (shift == nullptr), "gemm_xw: scale and shift must come together");
     DDMP_REQUIRE(n >= 0 && Cin > 0 && Cout > 0, "gemm_xw: bad shape");
     if (n == 0) return DDMP_OK;
+    DDMP_REQUIRE(X && W && H, "gemm_xw: null pointer");
+    DDMP_REQUIRE((scale == nullptr) == (shift == nullptr), "gemm_xw: scale and shift must come together");
     const bool tc_ok = tc_supported_xw(n, Cin, Cout) && workspace != nullptr;
     if (backend == DDMP_GEMM_TC && !tc_ok) {
         set_error("gemm_xw: tcgen05 path does not support n=%lld Cin=%d Cout=%d", (long long)n, Cin, Cout);
@@ -66,9 +66,9 @@ int ddmp_gemm_xw(const float* X, const int32_t* row_map, const float* scale, con
 int ddmp_gemm_dx(const float* dH, const float* W, float* gX, void* workspace, int64_t workspace_bytes, int64_t n,
                  int32_t Cin, int32_t Cout, int backend, void* stream) {
     using namespace ddmp;
-    DDMP_REQUIRE(dH && W && gX, "gemm_dx: null pointer");
     DDMP_REQUIRE(n >= 0 && Cin > 0 && Cout > 0, "gemm_dx: bad shape");
     if (n == 0) return DDMP_OK;
+    DDMP_REQUIRE(dH && W && gX, "gemm_dx: null pointer");
     const bool tc_ok = tc_supported_dx(n, Cin, Cout) && workspace != nullptr;
     if (backend == DDMP_GEMM_TC && !tc_ok) {
         set_error("gemm_dx: tcgen05 path does not support n=%lld Cin=%d Cout=%d", (long long)n, Cin, Cout);

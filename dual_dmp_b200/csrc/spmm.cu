@@ -192,9 +192,9 @@ int ddmp_gcn_edge_weights(const int32_t* rowptr, const int32_t* col, float* w, i
 int ddmp_spmm_gcn(const int32_t* rowptr, const int32_t* col, const float* w, const float* H, const float* bias,
                   float* Y, float* stats_partials, int64_t n, int32_t C, void* stream) {
     using namespace ddmp;
-    DDMP_REQUIRE(rowptr && col && w && H && Y, "spmm_gcn: null pointer");
     DDMP_REQUIRE(n >= 0 && C > 0, "spmm_gcn: bad shape n=%lld C=%d", (long long)n, C);
     if (n == 0) return DDMP_OK;
+    DDMP_REQUIRE(rowptr && col && w && H && Y, "spmm_gcn: null pointer");
     cudaStream_t st = as_stream(stream);
     switch (C) {
         case 32: return launch_spmm<32>(rowptr, col, w, H, bias, Y, stats_partials, n, st);
