@@ -8,6 +8,8 @@
 // coalesced load per G entries (lane j takes entry j) and broadcast with group-scoped shuffles.  A CTA of 256
 // threads walks `rows_per_block` consecutive rows (consecutive groups take consecutive rows, so neighbour rows
 // gathered by one CTA overlap in L1).  Roofline: HBM; algorithmic bytes 4*[(n+1) + 2*nnz + 2*n*C].
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace ddmp {
@@ -16,7 +18,7 @@ template <int C, bool STATS, bool BIAS>
 __global__ void __launch_bounds__(256, STATS ? 3 : 4)
 spmm_gcn_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const float* __restrict__ w,
                 const float* __restrict__ H, const float* __restrict__ bias, float* __restrict__ Y,
-                float* __restrict__ partials, int64_t n, int rows_per_block) {
+                float* __restrict__ partials, int64_t n, int rows_per_block, int blocks_per_cta) {
     constexpr int G = (C / 4 < 32) ? (C / 4) : 32;
     constexpr int NV = C / (4 * G);
     constexpr int GROUPS = 256 / G;
@@ -27,9 +29,6 @@ spmm_gcn_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, con
     const int gid = threadIdx.x / G;
     const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((lane / G) * G));
 
-    const int64_t row0 = (int64_t)blockIdx.x * rows_per_block;
-    const int64_t row_end = (row0 + rows_per_block < n) ? (row0 + rows_per_block) : n;
-
     float4 bsum[NV];
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
@@ -39,6 +38,13 @@ spmm_gcn_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, con
     // registers costs 8*NV registers and halves the occupancy of the widest instantiation: ncu, profiles/)
     __shared__ __align__(16) float red[STATS ? GROUPS * 2 * C : 4];
     float* myred = red + gid * 2 * C;
+    // A CTA walks `blocks_per_cta` consecutive row blocks (1 by default, see launch_spmm).
+    const int64_t nblk = (n + rows_per_block - 1) / rows_per_block;
+    const int64_t blk_begin = (int64_t)blockIdx.x * blocks_per_cta;
+    const int64_t blk_end = (blk_begin + blocks_per_cta < nblk) ? (blk_begin + blocks_per_cta) : nblk;
+    for (int64_t blk = blk_begin; blk < blk_end; ++blk) {
+    const int64_t row0 = blk * rows_per_block;
+    const int64_t row_end = (row0 + rows_per_block < n) ? (row0 + rows_per_block) : n;
     if (STATS) {
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
@@ -123,14 +129,16 @@ spmm_gcn_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, con
     if (STATS) {
         // combine the GROUPS row groups of this CTA channel-wise in a fixed order
         __syncthreads();
-        float* outp = partials + (int64_t)blockIdx.x * 2 * C;
+        float* outp = partials + blk * 2 * C;
         for (int i = threadIdx.x; i < 2 * C; i += 256) {
             float t = 0.f;
 #pragma unroll 8
             for (int g = 0; g < GROUPS; ++g) t += red[g * 2 * C + i];
             outp[i] = t;
         }
+        __syncthreads();
     }
+    }   // row blocks of this CTA
 }
 
 // Any width: one warp per row, lanes stride over channels (operator-level GCNConv with unusual widths).
@@ -167,13 +175,20 @@ template <int C>
 static int launch_spmm(const int* rowptr, const int* col, const float* w, const float* H, const float* bias,
                        float* Y, float* partials, int64_t n, cudaStream_t st) {
     const int rpb = ddmp_rows_per_block(C);
-    const unsigned grid = (unsigned)ceil_div(n, rpb);
+    const int64_t nblk = ceil_div(n, rpb);
+    // consecutive row blocks per CTA (DDMP_SPMM_CHUNK).  Default 1: walking 4 or 8 neighbouring blocks per CTA to
+    // keep gathered rows in L1 measured 9 % SLOWER step-weighted on B200 (3,565 vs 3,927 GB/s, scripts/bench_spmm.py)
+    // -- fewer, longer CTAs lose more to the tail than the extra L1 hits win back.
+    static const int chunk_env = [] { const char* e = getenv("DDMP_SPMM_CHUNK"); return e ? atoi(e) : 1; }();
+    int bpc = chunk_env < 1 ? 1 : chunk_env;
+    while (bpc > 1 && ceil_div(nblk, bpc) < 8 * kNumSMs) --bpc;
+    const unsigned grid = (unsigned)ceil_div(nblk, bpc);
     if (partials) {
-        if (bias) spmm_gcn_kernel<C, true, true><<<grid, 256, 0, st>>>(rowptr, col, w, H, bias, Y, partials, n, rpb);
-        else spmm_gcn_kernel<C, true, false><<<grid, 256, 0, st>>>(rowptr, col, w, H, bias, Y, partials, n, rpb);
+        if (bias) spmm_gcn_kernel<C, true, true><<<grid, 256, 0, st>>>(rowptr, col, w, H, bias, Y, partials, n, rpb, bpc);
+        else spmm_gcn_kernel<C, true, false><<<grid, 256, 0, st>>>(rowptr, col, w, H, bias, Y, partials, n, rpb, bpc);
     } else {
-        if (bias) spmm_gcn_kernel<C, false, true><<<grid, 256, 0, st>>>(rowptr, col, w, H, bias, Y, partials, n, rpb);
-        else spmm_gcn_kernel<C, false, false><<<grid, 256, 0, st>>>(rowptr, col, w, H, bias, Y, partials, n, rpb);
+        if (bias) spmm_gcn_kernel<C, false, true><<<grid, 256, 0, st>>>(rowptr, col, w, H, bias, Y, partials, n, rpb, bpc);
+        else spmm_gcn_kernel<C, false, false><<<grid, 256, 0, st>>>(rowptr, col, w, H, bias, Y, partials, n, rpb, bpc);
     }
     return check_launch("spmm_gcn");
 }
