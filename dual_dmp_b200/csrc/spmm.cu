@@ -15,7 +15,7 @@
 namespace ddmp {
 
 template <int C, bool STATS, bool BIAS>
-__global__ void __launch_bounds__(256, STATS ? 3 : 4)
+__global__ void __launch_bounds__(256, (STATS || C >= 512) ? 3 : 4)
 spmm_gcn_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const float* __restrict__ w,
                 const float* __restrict__ H, const float* __restrict__ bias, float* __restrict__ Y,
                 float* __restrict__ partials, int64_t n, int rows_per_block, int blocks_per_cta) {
@@ -53,17 +53,36 @@ spmm_gcn_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, con
         }
     }
 
-    for (int64_t r = row0 + gid; r < row_end; r += GROUPS) {
-        const int start = __ldg(rowptr + r);
-        const int end = __ldg(rowptr + r + 1);
+    // Software pipeline over the rows of a group: (rowptr, first col/w chunk) of the NEXT row are fetched while the
+    // gathers of the current row are in flight, so the rowptr -> col -> H dependent-load chain is paid once per
+    // group instead of once per row (narrow widths are latency-, not bandwidth-bound).
+    int64_t r = row0 + gid;
+    int start = 0, end = 0, myc = 0;
+    float myw = 0.f;
+    if (r < row_end) {
+        start = __ldg(rowptr + r);
+        end = __ldg(rowptr + r + 1);
+        const int kk = start + lg;
+        if (kk < end) { myc = __ldg(col + kk); myw = __ldg(w + kk); }
+    }
+    for (; r < row_end; r += GROUPS) {
+        const int64_t rn = r + GROUPS;
+        int nstart = 0, nend = 0, nmyc = 0;
+        float nmyw = 0.f;
+        if (rn < row_end) {
+            nstart = __ldg(rowptr + rn);
+            nend = __ldg(rowptr + rn + 1);
+        }
         float4 acc[NV];
 #pragma unroll
         for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
 
         for (int k0 = start; k0 < end; k0 += G) {
-            const int kk = k0 + lg;
-            const int myc = (kk < end) ? __ldg(col + kk) : 0;
-            const float myw = (kk < end) ? __ldg(w + kk) : 0.f;
+            if (k0 != start) {                       // rows longer than G entries: further chunks are loaded here
+                const int kk = k0 + lg;
+                myc = (kk < end) ? __ldg(col + kk) : 0;
+                myw = (kk < end) ? __ldg(w + kk) : 0.f;
+            }
             const int cnt = (end - k0 < G) ? (end - k0) : G;
             int j = 0;
             for (; j + U <= cnt; j += U) {
@@ -80,6 +99,10 @@ spmm_gcn_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, con
                     const float* hp = H + (int64_t)cj[u] * C;
 #pragma unroll
                     for (int v = 0; v < NV; ++v) x[u][v] = ldg4(hp + (v * G + lg) * 4);
+                }
+                if (k0 == start && j == 0 && rn < row_end) {   // next row's first chunk, behind the gathers in flight
+                    const int kk = nstart + lg;
+                    if (kk < nend) { nmyc = __ldg(col + kk); nmyw = __ldg(w + kk); }
                 }
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
@@ -106,6 +129,10 @@ spmm_gcn_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, con
                 }
             }
         }
+        if (rn < row_end && (end - start) < U) {     // short row: the prefetch slot inside the unrolled loop was skipped
+            const int kk = nstart + lg;
+            if (kk < nend) { nmyc = __ldg(col + kk); nmyw = __ldg(w + kk); }
+        }
         float* yp = Y + r * C;
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
@@ -124,6 +151,7 @@ spmm_gcn_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, con
                 st4(myred + C + (v * G + lg) * 4, q);
             }
         }
+        start = nstart; end = nend; myc = nmyc; myw = nmyw;
     }
 
     if (STATS) {
