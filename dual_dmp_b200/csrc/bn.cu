@@ -7,16 +7,18 @@
 
 namespace ddmp {
 
-// One CTA = 32 channels x kFinLanes block-lanes (1024 threads).  sums[s] (double) for channel c, valid in all
-// threads; lane ty accumulates blocks ty, ty+kFinLanes, ... and the lanes are combined in lane order, so the
-// summation order is fixed.
-constexpr int kFinLanes = 32;
-constexpr int kFinThreads = 32 * kFinLanes;
+// One CTA = kFinCh channels x kFinLanes block-lanes (1024 threads): lane ty accumulates blocks ty, ty+kFinLanes, ...
+// in float64 and the lanes are combined in lane order, so the summation order is fixed.  8 channels per CTA (one
+// 32-byte sector per block row) keeps the loads sector-exact while giving C/8 CTAs: with 32 channels per CTA the
+// 512-wide finalize ran on 16 CTAs and took 59 us per launch (ncu launch list, profiles/).
+constexpr int kFinCh = 8;
+constexpr int kFinLanes = 128;
+constexpr int kFinThreads = kFinCh * kFinLanes;
 template <int SETS>
 __device__ __forceinline__ void reduce_partials(const float* __restrict__ partials, int64_t nblk, int C, int c,
                                                 double (&out)[SETS]) {
-    __shared__ double red[kFinLanes][SETS][33];
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    __shared__ double red[kFinLanes][SETS][kFinCh + 1];
+    const int tx = threadIdx.x % kFinCh, ty = threadIdx.x / kFinCh;
     double acc[SETS];
 #pragma unroll
     for (int s = 0; s < SETS; ++s) acc[s] = 0.0;
@@ -55,10 +57,10 @@ bn_stats_finalize_kernel(const float* __restrict__ partials, int64_t nblk, int64
                          const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float momentum,
                          float* running_mean, float* running_var, float* mean, float* rstd, float* scale,
                          float* shift) {
-    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int c = blockIdx.x * kFinCh + (threadIdx.x % kFinCh);
     double s[2];
     reduce_partials<2>(partials, nblk, C, c, s);
-    if (threadIdx.x < 32 && c < C) {
+    if (threadIdx.x < kFinCh && c < C) {
         const double m = s[0] / (double)n;
         double var = s[1] / (double)n - m * m;
         if (var < 0.0) var = 0.0;
@@ -80,10 +82,10 @@ bn_stats_finalize_kernel(const float* __restrict__ partials, int64_t nblk, int64
 __global__ void __launch_bounds__(kFinThreads)
 bn_bwd_finalize_kernel(const float* __restrict__ partials, int64_t nblk, int64_t n, int C, float* dgamma,
                        float* dbeta, float* c1, float* c2) {
-    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int c = blockIdx.x * kFinCh + (threadIdx.x % kFinCh);
     double s[2];
     reduce_partials<2>(partials, nblk, C, c, s);
-    if (threadIdx.x < 32 && c < C) {
+    if (threadIdx.x < kFinCh && c < C) {
         dbeta[c] = (float)s[0];
         dgamma[c] = (float)s[1];
         c1[c] = (float)(s[0] / (double)n);
@@ -94,10 +96,10 @@ bn_bwd_finalize_kernel(const float* __restrict__ partials, int64_t nblk, int64_t
 template <int SETS>
 __global__ void __launch_bounds__(kFinThreads)
 colsum_finalize_kernel(const float* __restrict__ partials, int64_t nblk, int C, float* out) {
-    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int c = blockIdx.x * kFinCh + (threadIdx.x % kFinCh);
     double s[SETS];
     reduce_partials<SETS>(partials, nblk, C, c, s);
-    if (threadIdx.x < 32 && c < C) {
+    if (threadIdx.x < kFinCh && c < C) {
 #pragma unroll
         for (int k = 0; k < SETS; ++k) out[k * C + c] = (float)s[k];
     }
@@ -212,7 +214,7 @@ int ddmp_bn_stats_finalize(const float* partials, int64_t nblk, int64_t n, int32
     using namespace ddmp;
     DDMP_REQUIRE(partials && gamma && beta && mean && rstd && scale && shift, "bn_stats_finalize: null pointer");
     DDMP_REQUIRE(n > 0 && C > 0 && nblk > 0, "bn_stats_finalize: bad shape");
-    bn_stats_finalize_kernel<<<(unsigned)ceil_div(C, 32), kFinThreads, 0, as_stream(stream)>>>(
+    bn_stats_finalize_kernel<<<(unsigned)ceil_div(C, kFinCh), kFinThreads, 0, as_stream(stream)>>>(
         partials, nblk, n, C, gamma, beta, eps, momentum, running_mean, running_var, mean, rstd, scale, shift);
     return check_launch("bn_stats_finalize");
 }
@@ -231,7 +233,7 @@ int ddmp_bn_bwd_finalize(const float* partials, int64_t nblk, int64_t n, int32_t
     using namespace ddmp;
     DDMP_REQUIRE(partials && dgamma && dbeta && c1 && c2, "bn_bwd_finalize: null pointer");
     DDMP_REQUIRE(n > 0 && C > 0 && nblk > 0, "bn_bwd_finalize: bad shape");
-    bn_bwd_finalize_kernel<<<(unsigned)ceil_div(C, 32), kFinThreads, 0, as_stream(stream)>>>(partials, nblk, n, C, dgamma,
+    bn_bwd_finalize_kernel<<<(unsigned)ceil_div(C, kFinCh), kFinThreads, 0, as_stream(stream)>>>(partials, nblk, n, C, dgamma,
                                                                                     dbeta, c1, c2);
     return check_launch("bn_bwd_finalize");
 }
@@ -266,7 +268,7 @@ int ddmp_colsum_partials(const float* X, float* partials, int64_t n, int32_t C, 
 int ddmp_colsum_finalize(const float* partials, int64_t nblk, int32_t sets, int32_t C, float* out, void* stream) {
     using namespace ddmp;
     DDMP_REQUIRE(partials && out && nblk > 0 && C > 0, "colsum_finalize: bad arguments");
-    const unsigned grid = (unsigned)ceil_div(C, 32);
+    const unsigned grid = (unsigned)ceil_div(C, kFinCh);
     cudaStream_t st = as_stream(stream);
     if (sets == 1) colsum_finalize_kernel<1><<<grid, kFinThreads, 0, st>>>(partials, nblk, C, out);
     else if (sets == 2) colsum_finalize_kernel<2><<<grid, kFinThreads, 0, st>>>(partials, nblk, C, out);
