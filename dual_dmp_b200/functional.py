@@ -16,6 +16,7 @@ SLOPE = 0.01        # nn.LeakyReLU() default (reference util/networks.py:44,105)
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
 GEMM_BACKEND = 0    # DDMP_GEMM_AUTO; tests may set 1 (FFMA) / 2 (tcgen05)
+FUSE_BN_SPMM = True  # backward: recompute dY inside the aggregation kernel instead of materialising it
 
 HEAD_POS, HEAD_NORM = 0, 1
 
@@ -140,6 +141,27 @@ def bn_lrelu_backward(gX, Y, stats, dY_out=None, comm=None):
     return dY, small[0], small[1], small[4]
 
 
+def bn_bwd_spmm_fused(graph, gX, Y, stats, dH_out=None):
+    """BatchNorm/LeakyReLU backward + backward aggregation with dY never materialised:
+    reduce (sum gZ, sum gZ*xhat) -> finalize -> ddmp_spmm_bn_bwd.  Returns (dH, dgamma, dbeta, dbias)."""
+    n, C = Y.shape
+    dev = Y.device
+    st = stream_ptr(dev)
+    nblk = num_row_blocks(n, C)
+    partials = torch.empty(nblk, 2, C, dtype=torch.float32, device=dev)
+    small = torch.empty(5, C, dtype=torch.float32, device=dev)             # dgamma, dbeta, c1, c2, dbias
+    mean, rstd, scale, shift = stats[0], stats[1], stats[2], stats[3]
+    lib.call("ddmp_bn_bwd_reduce", ptr(gX), ptr(Y), ptr(mean), ptr(rstd), ptr(scale), ptr(shift), SLOPE,
+             ptr(partials), n, C, st)
+    lib.call("ddmp_bn_bwd_finalize", ptr(partials), nblk, n, C, ptr(small[0]), ptr(small[1]), ptr(small[2]),
+             ptr(small[3]), st)
+    dH = dH_out if dH_out is not None else torch.empty_like(Y)
+    lib.call("ddmp_spmm_bn_bwd", ptr(graph.rowptr), ptr(graph.col), ptr(graph.w), ptr(gX), ptr(Y), ptr(mean),
+             ptr(rstd), ptr(scale), ptr(shift), ptr(small[2]), ptr(small[3]), SLOPE, ptr(dH), ptr(partials), n, C, st)
+    lib.call("ddmp_colsum_finalize", ptr(partials), nblk, 1, C, ptr(small[4]), st)
+    return dH, small[0], small[1], small[4]
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # operator-level GCNConv  (drop-in for torch_geometric.nn.GCNConv.forward, reference util/networks.py:15-26)
 # ---------------------------------------------------------------------------------------------------------------------
@@ -259,7 +281,8 @@ class GcnNetFunction(torch.autograd.Function):
         comm = graph if hasattr(graph, "exchange") else None
         n_ext = graph.n_ext if comm is not None else n
         bufA = torch.empty(n * cmax, dtype=torch.float32, device=dev)      # gX (grad wrt activated layer output)
-        bufB = torch.empty(n_ext * cmax, dtype=torch.float32, device=dev)  # dY  ([owned | halo] rows)
+        fused = comm is None and FUSE_BN_SPMM and graph.symmetric
+        bufB = None if fused else torch.empty(n_ext * cmax, dtype=torch.float32, device=dev)   # dY ([owned | halo])
         bufC = torch.empty(n * cmax, dtype=torch.float32, device=dev)      # dH
         gX = bufA[: n * 32].view(n, 32)
         lib.call("ddmp_head_bwd", kind, ptr(g_out), ptr(graph.perm), ptr(W1), ptr(W2), ptr(ctx.h_save),
@@ -273,12 +296,15 @@ class GcnNetFunction(torch.autograd.Function):
         grads = [None] * (4 * L)
         for l in range(L - 1, -1, -1):
             cout, cin = Ws[l].shape
-            dY = bufB[: n_ext * cout].view(n_ext, cout)
-            _, dgamma, dbeta, dbias = bn_lrelu_backward(gX, Ys[l], stats[l], dY_out=dY, comm=comm)
-            if comm is not None:
-                comm.exchange(dY)                   # A_hat symmetric: the backward needs dY of the halo rows
             dH = bufC[: n * cout].view(n, cout)
-            spmm_gcn(graph, dY, transposed=True, out=dH, n_rows=n)
+            if comm is None and FUSE_BN_SPMM and graph.symmetric and cout in (32, 64, 128, 256, 512):
+                _, dgamma, dbeta, dbias = bn_bwd_spmm_fused(graph, gX, Ys[l], stats[l], dH_out=dH)
+            else:
+                dY = bufB[: n_ext * cout].view(n_ext, cout)
+                _, dgamma, dbeta, dbias = bn_lrelu_backward(gX, Ys[l], stats[l], dY_out=dY, comm=comm)
+                if comm is not None:
+                    comm.exchange(dY)               # A_hat symmetric: the backward needs dY of the halo rows
+                spmm_gcn(graph, dY, transposed=True, out=dH, n_rows=n)
             if l == 0:
                 gW = gemm_dw(dH, x_in, cin, row_map=graph.perm)
             else:

@@ -65,6 +65,14 @@ int ddmp_gcn_edge_weights(const int32_t* rowptr, const int32_t* col, float* w, i
 int ddmp_spmm_gcn(const int32_t* rowptr, const int32_t* col, const float* w, const float* H, const float* bias,
                   float* Y, float* stats_partials, int64_t n, int32_t C, void* stream);
 
+/* Backward aggregation fused with ddmp_bn_bwd_apply:  dH = A_hat * dY  with dY recomputed on the fly from the gathered
+ * rows of gX and Y (dY is never materialised); optional colsum_partials[b][0][c] = column sums of dY (conv bias
+ * gradient).  Symmetric graphs only (the CSR is used as its own transpose); C in {32,64,128,256,512}. */
+int ddmp_spmm_bn_bwd(const int32_t* rowptr, const int32_t* col, const float* w, const float* gX, const float* Y,
+                     const float* mean, const float* rstd, const float* scale, const float* shift, const float* c1,
+                     const float* c2, float slope, float* dH, float* colsum_partials, int64_t n, int32_t C,
+                     void* stream);
+
 /* ---- BatchNorm1d (training mode) + LeakyReLU ------------------------------------------------------------ */
 /* partials [nblk][2][C] -> batch mean / biased var; rstd = 1/sqrt(var+eps); scale = gamma*rstd;
  * shift = beta - mean*scale; running stats updated in place when non-NULL (momentum, unbiased var).

@@ -321,3 +321,31 @@ def test_fused_clip_adam_matches_torch():
             assert rel_err(q, p) < 2e-6, (it, rel_err(q, p))
     assert int(opt.step_count) == 5
     assert all(q.data_ptr() >= opt.flat.data_ptr() for q in mine)         # parameters are views of the flat buffer
+
+
+@pytest.mark.parametrize("C", [32, 64, 128, 256, 512])
+@pytest.mark.parametrize("which", ["vg", "fg"])
+def test_fused_bn_backward_aggregation(graphs, C, which):
+    """ddmp_spmm_bn_bwd (dY recomputed inside the gather) == bn_bwd_apply followed by spmm_gcn"""
+    from dual_dmp_b200 import functional as F_
+    g = graphs["open"][which]
+    torch.manual_seed(C)
+    n = g.n
+    Y = (torch.randn(n, C) * 1.5 + 0.3).to(DEV)
+    gX = torch.randn(n, C, device=DEV)
+    st = F_.bn_stats_finalize(F_.spmm_gcn(GcnGraphIdentity(n), Y, stats=True)[1], n,
+                              (torch.rand(C) + 0.5).to(DEV), torch.randn(C).to(DEV))
+    dY, dgamma, dbeta, dbias = F_.bn_lrelu_backward(gX, Y, st)
+    dH_ref = F_.spmm_gcn(g, dY, transposed=True)
+    dH, dgamma2, dbeta2, dbias2 = F_.bn_bwd_spmm_fused(g, gX, Y, st)
+    e = rel_err(dH, dH_ref)
+    report(f"fused bn+spmm bwd C={C} {which}", e)
+    assert e < 2e-6 and torch.equal(dgamma, dgamma2) and torch.equal(dbeta, dbeta2)
+    assert (dbias2 - dbias).abs().max() <= 1e-5 * dY.abs().sum(dim=0).max()
+    a, _, _, _ = F_.bn_bwd_spmm_fused(g, gX, Y, st)
+    assert torch.equal(a, dH)
+
+
+def GcnGraphIdentity(n):
+    from dual_dmp_b200.graph import GcnGraph
+    return GcnGraph(torch.zeros(2, 0, dtype=torch.long), n, DEV, reorder=False)
