@@ -16,7 +16,10 @@ SLOPE = 0.01        # nn.LeakyReLU() default (reference util/networks.py:44,105)
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
 GEMM_BACKEND = 0    # DDMP_GEMM_AUTO; tests may set 1 (FFMA) / 2 (tcgen05)
-FUSE_BN_SPMM = True  # backward: recompute dY inside the aggregation kernel instead of materialising it
+# backward: recompute dY inside the aggregation kernel (ddmp_spmm_bn_bwd) instead of materialising it.  OFF: measured
+# on B200 at 1M faces the doubled gather volume through L2 costs more than the two saved passes over dY (C=512:
+# 1.82 vs 1.37 ms vertex graph, 2.87 vs 2.52 ms face graph; scripts/bench_bn_spmm.py) -- kept for narrower graphs.
+FUSE_BN_SPMM = False
 
 HEAD_POS, HEAD_NORM = 0, 1
 
