@@ -47,6 +47,12 @@ class DualStep:
             self.opt_norm = torch.optim.Adam(normnet.parameters(), lr=norm_lr, capturable=self.capture)
         self._graphs: dict = {}
         self._static_loss: dict = {}
+        # streaming inputs (prefetch): staging copies of the per-step inputs, filled by a copy stream
+        self._stage = None
+        self._copy_stream = None
+        self._stage_ready = None
+        self._stage_free = None
+        self._pending = False
         self._eager_calls = 0
         self.pos = None      # outputs of the most recent step (static tensors when captured)
         self.norm = None
@@ -97,9 +103,53 @@ class DualStep:
             self._static_loss[bnf_off] = self._body(bnf_off)
         self._graphs[bnf_off] = g
 
+    # ---- streaming inputs: host -> staging on a copy stream, overlapped with the running step ----------------------
+    def _static_inputs(self):
+        return {"z1": self.dataset.z1, "z2": self.dataset.z2, "x_pos": self.dataset.x_pos,
+                "tgt_vs": self.tgt_vs, "tgt_fn": self.tgt_fn}
+
+    def prefetch(self, dataset_host, tgt_vs_host, tgt_fn_host) -> int:
+        """Start uploading the inputs of the NEXT ``step`` (the tensors the reference loop moves to the device every
+        iteration: ``z1``, ``z2``, ``x_pos`` and the float64 targets) from pinned host memory.  The copies run on a
+        dedicated stream into staging buffers, so they overlap the iteration that is executing; the next ``step``
+        waits for them, moves staging -> static inputs (device-to-device) and runs.  Returns the bytes enqueued."""
+        host = {"z1": dataset_host.z1, "z2": dataset_host.z2, "x_pos": dataset_host.x_pos,
+                "tgt_vs": tgt_vs_host, "tgt_fn": tgt_fn_host}
+        static = self._static_inputs()
+        if self._stage is None:
+            self._stage = {k: torch.empty_like(v) for k, v in static.items()}
+            self._copy_stream = torch.cuda.Stream(self.device)
+            self._stage_ready = torch.cuda.Event()
+            self._stage_free = torch.cuda.Event()
+            self._stage_free.record(torch.cuda.current_stream(self.device))
+        nbytes = 0
+        self._copy_stream.wait_event(self._stage_free)       # the previous staging -> static move has been issued
+        with torch.no_grad(), torch.cuda.stream(self._copy_stream):
+            for k, dst in self._stage.items():
+                src = host[k]
+                if src.shape != dst.shape or src.dtype != dst.dtype:
+                    raise ValueError(f"prefetch: {k} is {tuple(src.shape)} {src.dtype}, expected "
+                                     f"{tuple(dst.shape)} {dst.dtype}")
+                dst.copy_(src, non_blocking=True)
+                nbytes += src.numel() * src.element_size()
+            self._stage_ready.record(self._copy_stream)
+        self._pending = True
+        return nbytes
+
+    def _consume_prefetch(self) -> None:
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(self._stage_ready)
+        with torch.no_grad():
+            for k, dst in self._static_inputs().items():
+                dst.copy_(self._stage[k], non_blocking=True)
+        self._stage_free.record(cur)
+        self._pending = False
+
     def step(self, epoch: int) -> torch.Tensor:
         """one training iteration; returns the (device, float64) loss without synchronising"""
         bnf_off = epoch <= self.bnf_warmup_epochs
+        if self._pending:
+            self._consume_prefetch()
         if not self.capture:
             return self._body(bnf_off)
         if bnf_off not in self._graphs:

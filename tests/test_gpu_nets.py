@@ -214,6 +214,50 @@ def test_dual_step_cuda_graph_matches_eager_and_oracle():
     assert graph_step.pos.shape == (len(n_mesh.vs), 3) and torch.isfinite(graph_step.pos).all()
 
 
+def test_dual_step_streamed_inputs():
+    """DualStep.prefetch: per-step uploads from pinned host memory on the copy stream.  Streaming the SAME inputs
+    reproduces the resident run bit for bit; streaming different inputs reaches the captured graph (the loss changes
+    to what a resident run on those inputs gives)"""
+    import copy
+    from dual_dmp_b200.step import DualStep
+    from dual_dmp_b200.util.datamaker import dataset_from_meshes
+    n_mesh, s_mesh, _ = small_case("ico", 8)
+    ds = dataset_from_meshes(n_mesh, s_mesh)
+    _, _, pd, nd = _pair(5)
+    pd2, nd2 = copy.deepcopy(pd), copy.deepcopy(nd)
+    pd3, nd3 = copy.deepcopy(pd), copy.deepcopy(nd)
+    resident = DualStep(pd, nd, ds, n_mesh)
+    streamed = DualStep(pd2, nd2, ds, n_mesh)
+    host = copy.copy(ds).pin_memory()
+    vs_h, fn_h = torch.from_numpy(n_mesh.vs).pin_memory(), torch.from_numpy(n_mesh.fn).pin_memory()
+    a, b = [], []
+    for ep in range(101, 108):
+        a.append(resident.step(ep).clone())
+        nbytes = streamed.prefetch(host, vs_h, fn_h)
+        b.append(streamed.step(ep).clone())
+    torch.cuda.synchronize()
+    assert nbytes == sum(t.numel() * t.element_size() for t in (host.z1, host.z2, host.x_pos, vs_h, fn_h))
+    assert [float(x) for x in a] == [float(x) for x in b]
+    # different inputs, once the graph is live: compare with a resident stepper built on those inputs
+    ds2 = copy.copy(ds)
+    ds2.z1 = ds.z1.detach() * 1.25
+    ds2.z2 = ds.z2.detach().clone()
+    ds2.z2[:, 3:] *= 0.75                          # centroids (which order the face graph) untouched
+    ds2.x = ds2.z1
+    other = DualStep(pd3, nd3, ds2, n_mesh)
+    fresh = DualStep(copy.deepcopy(pd3), copy.deepcopy(nd3), ds, n_mesh)
+    host2 = copy.copy(ds2).pin_memory()
+    lo, lf = [], []
+    for ep in range(101, 107):
+        lo.append(other.step(ep).clone())
+        fresh.prefetch(host2, vs_h, fn_h)          # built on ds, fed ds2 from the host every step
+        lf.append(fresh.step(ep).clone())
+    torch.cuda.synchronize()
+    assert [float(x) for x in lo] == [float(x) for x in lf]
+    with pytest.raises(ValueError):
+        fresh.prefetch(host2, vs_h[:-1], fn_h)
+
+
 @pytest.mark.parametrize("name", ["tetra", "strip2", "ico3", "open4"])
 def test_tiny_and_boundary_meshes_match_oracle(golden_dir, name):
     """edge cases of the reference's own fixtures: 4-vertex / 2-face meshes (fewer rows than one tile), an open mesh
