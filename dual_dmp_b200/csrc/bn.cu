@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(kFinThreads)
 bn_stats_finalize_kernel(const float* __restrict__ partials, int64_t nblk, int64_t n, int C,
                          const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float momentum,
                          float* running_mean, float* running_var, float* mean, float* rstd, float* scale,
-                         float* shift) {
+                         float* shift, float* bound) {
     const int c = blockIdx.x * kFinCh + (threadIdx.x % kFinCh);
     double s[2];
     reduce_partials<2>(partials, nblk, C, c, s);
@@ -71,6 +71,9 @@ bn_stats_finalize_kernel(const float* __restrict__ partials, int64_t nblk, int64
         rstd[c] = r;
         scale[c] = sc;
         shift[c] = beta[c] - mf * sc;
+        // no sample of a batch of n lies more than sqrt(n-1) (biased) standard deviations from the batch mean, so
+        // |scale*y + shift| <= |gamma|*sqrt(n-1) + |beta| for every row: the operand bound of the fp16-split GEMMs
+        if (bound) bound[c] = fabsf(gamma[c]) * sqrtf((float)(n > 1 ? n - 1 : 1)) + fabsf(beta[c]);
         if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mf;
         if (running_var) {
             const double unbiased = (n > 1) ? var * ((double)n / (double)(n - 1)) : var;
@@ -210,12 +213,12 @@ extern "C" {
 
 int ddmp_bn_stats_finalize(const float* partials, int64_t nblk, int64_t n, int32_t C, const float* gamma,
                            const float* beta, float eps, float momentum, float* running_mean, float* running_var,
-                           float* mean, float* rstd, float* scale, float* shift, void* stream) {
+                           float* mean, float* rstd, float* scale, float* shift, float* bound, void* stream) {
     using namespace ddmp;
     DDMP_REQUIRE(partials && gamma && beta && mean && rstd && scale && shift, "bn_stats_finalize: null pointer");
     DDMP_REQUIRE(n > 0 && C > 0 && nblk > 0, "bn_stats_finalize: bad shape");
     bn_stats_finalize_kernel<<<(unsigned)ceil_div(C, kFinCh), kFinThreads, 0, as_stream(stream)>>>(
-        partials, nblk, n, C, gamma, beta, eps, momentum, running_mean, running_var, mean, rstd, scale, shift);
+        partials, nblk, n, C, gamma, beta, eps, momentum, running_mean, running_var, mean, rstd, scale, shift, bound);
     return check_launch("bn_stats_finalize");
 }
 

@@ -15,24 +15,30 @@ bool tc_supported_dx(int64_t n, int32_t Cin, int32_t Cout);
 bool tc_supported_dw(int64_t n, int32_t Cin, int32_t Cout);
 int64_t tc_gemm_nt_workspace_bytes(int32_t, int32_t);
 int tc_gemm_xw(const float*, const int32_t*, const float*, const float*, float, const float*, float*, void*, int64_t,
-               int64_t, int32_t, int32_t, cudaStream_t);
-int tc_gemm_dx(const float*, const float*, float*, void*, int64_t, int64_t, int32_t, int32_t, cudaStream_t);
+               int64_t, int32_t, int32_t, const float*, int64_t, cudaStream_t);
+int tc_gemm_dx(const float*, const float*, float*, void*, int64_t, int64_t, int32_t, int32_t, const float*, int64_t,
+               cudaStream_t);
 int64_t tc_gemm_dw_workspace_bytes(int64_t, int32_t, int32_t);
 int tc_gemm_dw(const float*, const float*, const int32_t*, const float*, const float*, float, float*, void*,
-               int64_t, int64_t, int32_t, int32_t, cudaStream_t);
+               int64_t, int64_t, int32_t, int32_t, const float*, int64_t, const float*, int64_t, cudaStream_t);
 #else
 static bool tc_supported_xw(int64_t, int32_t, int32_t) { return false; }
 static bool tc_supported_dx(int64_t, int32_t, int32_t) { return false; }
 static bool tc_supported_dw(int64_t, int32_t, int32_t) { return false; }
 static int64_t tc_gemm_nt_workspace_bytes(int32_t, int32_t) { return 0; }
 static int tc_gemm_xw(const float*, const int32_t*, const float*, const float*, float, const float*, float*, void*,
-                      int64_t, int64_t, int32_t, int32_t, cudaStream_t) { return DDMP_ERR_UNSUPPORTED; }
-static int tc_gemm_dx(const float*, const float*, float*, void*, int64_t, int64_t, int32_t, int32_t, cudaStream_t) {
+                      int64_t, int64_t, int32_t, int32_t, const float*, int64_t, cudaStream_t) {
+    return DDMP_ERR_UNSUPPORTED;
+}
+static int tc_gemm_dx(const float*, const float*, float*, void*, int64_t, int64_t, int32_t, int32_t, const float*,
+                      int64_t, cudaStream_t) {
     return DDMP_ERR_UNSUPPORTED;
 }
 static int64_t tc_gemm_dw_workspace_bytes(int64_t, int32_t, int32_t) { return 0; }
 static int tc_gemm_dw(const float*, const float*, const int32_t*, const float*, const float*, float, float*, void*,
-                      int64_t, int64_t, int32_t, int32_t, cudaStream_t) { return DDMP_ERR_UNSUPPORTED; }
+                      int64_t, int64_t, int32_t, int32_t, const float*, int64_t, const float*, int64_t, cudaStream_t) {
+    return DDMP_ERR_UNSUPPORTED;
+}
 #endif
 }  // namespace ddmp
 
@@ -46,7 +52,7 @@ int64_t ddmp_gemm_workspace_bytes(int64_t n, int32_t Cin, int32_t Cout) {
 
 int ddmp_gemm_xw(const float* X, const int32_t* row_map, const float* scale, const float* shift, float slope,
                  const float* W, float* H, void* workspace, int64_t workspace_bytes, int64_t n, int32_t Cin,
-                 int32_t Cout, int backend, void* stream) {
+                 int32_t Cout, const float* amax, int64_t amax_len, int backend, void* stream) {
     using namespace ddmp;
     DDMP_REQUIRE(n >= 0 && Cin > 0 && Cout > 0, "gemm_xw: bad shape");
     if (n == 0) return DDMP_OK;
@@ -58,13 +64,13 @@ int ddmp_gemm_xw(const float* X, const int32_t* row_map, const float* scale, con
         return DDMP_ERR_UNSUPPORTED;
     }
     if (backend == DDMP_GEMM_TC || (backend == DDMP_GEMM_AUTO && tc_ok))
-        return tc_gemm_xw(X, row_map, scale, shift, slope, W, H, workspace, workspace_bytes, n, Cin, Cout,
-                          as_stream(stream));
+        return tc_gemm_xw(X, row_map, scale, shift, slope, W, H, workspace, workspace_bytes, n, Cin, Cout, amax,
+                          amax_len, as_stream(stream));
     return ffma_gemm_xw(X, row_map, scale, shift, slope, W, H, n, Cin, Cout, as_stream(stream));
 }
 
 int ddmp_gemm_dx(const float* dH, const float* W, float* gX, void* workspace, int64_t workspace_bytes, int64_t n,
-                 int32_t Cin, int32_t Cout, int backend, void* stream) {
+                 int32_t Cin, int32_t Cout, const float* amax, int64_t amax_len, int backend, void* stream) {
     using namespace ddmp;
     DDMP_REQUIRE(n >= 0 && Cin > 0 && Cout > 0, "gemm_dx: bad shape");
     if (n == 0) return DDMP_OK;
@@ -75,7 +81,7 @@ int ddmp_gemm_dx(const float* dH, const float* W, float* gX, void* workspace, in
         return DDMP_ERR_UNSUPPORTED;
     }
     if (backend == DDMP_GEMM_TC || (backend == DDMP_GEMM_AUTO && tc_ok))
-        return tc_gemm_dx(dH, W, gX, workspace, workspace_bytes, n, Cin, Cout, as_stream(stream));
+        return tc_gemm_dx(dH, W, gX, workspace, workspace_bytes, n, Cin, Cout, amax, amax_len, as_stream(stream));
     return ffma_gemm_dx(dH, W, gX, n, Cin, Cout, as_stream(stream));
 }
 
@@ -89,7 +95,8 @@ int64_t ddmp_gemm_dw_workspace_bytes(int64_t n, int32_t Cin, int32_t Cout) {
 
 int ddmp_gemm_dw(const float* dH, const float* X, const int32_t* row_map, const float* scale, const float* shift,
                  float slope, float* dW, void* workspace, int64_t workspace_bytes, int64_t n, int32_t Cin,
-                 int32_t Cout, int backend, void* stream) {
+                 int32_t Cout, const float* amax_dh, int64_t amax_dh_len, const float* amax_x, int64_t amax_x_len,
+                 int backend, void* stream) {
     using namespace ddmp;
     DDMP_REQUIRE(dH && X && dW, "gemm_dw: null pointer");
     DDMP_REQUIRE((scale == nullptr) == (shift == nullptr), "gemm_dw: scale and shift must come together");
@@ -101,7 +108,7 @@ int ddmp_gemm_dw(const float* dH, const float* X, const int32_t* row_map, const 
     }
     if (backend == DDMP_GEMM_TC || (backend == DDMP_GEMM_AUTO && tc_ok))
         return tc_gemm_dw(dH, X, row_map, scale, shift, slope, dW, workspace, workspace_bytes, n, Cin, Cout,
-                          as_stream(stream));
+                          amax_dh, amax_dh_len, amax_x, amax_x_len, as_stream(stream));
     return ffma_gemm_dw(dH, X, row_map, scale, shift, slope, dW, workspace, workspace_bytes, n, Cin, Cout,
                         as_stream(stream));
 }

@@ -10,6 +10,7 @@
 // into the 128-byte-swizzled UMMA canonical layout, one elected thread of a 9th warp issues the MMAs, and all
 // producer warps drain the TMEM accumulator in the epilogue.  Pipeline: `full`/`empty` mbarriers per smem stage,
 // tcgen05.commit releases a stage / publishes the accumulator.
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include <type_traits>
@@ -989,6 +990,609 @@ static int launch_nt3(const Nt2Args& g0, cudaStream_t st) {
     return check_launch("tc_gemm_nt3");
 }
 
+// ---- fp32 emulation with three fp16 MMAs (kind::f16) ----------------------------------------------------------------
+// x*s = hi + lo with hi = fp16(x*s), lo = fp16(x*s - hi): two round-to-nearest 11-bit pieces carry 22+ bits of x, so
+// hi*hi + hi*lo + lo*hi (fp32 accumulation in TMEM) has the accuracy of an fp32 product sum (measured: closer to the
+// float64 result than the 3xTF32 split, whose pieces are truncated).  kind::f16 issues at twice the kind::tf32 rate
+// and every operand byte count halves (shared-memory reads/writes, the weight image streamed from L2).
+// fp16 has 5 exponent bits, so each operand is multiplied by a power of two `s` (exact) chosen from an upper bound of
+// its magnitude: s*|x| < 2^15.  Elements more than 2^17 below the bound lose low bits of `lo` (absolute error
+// <= 2^-40 of the bound).  The caller supplies the bound as a device array whose maximum is taken in-kernel
+// (`amax`): the BatchNorm bound |gamma|*sqrt(n-1)+|beta| for activated inputs (no sample is more than sqrt(n-1)
+// biased standard deviations from the batch mean), per-row-block maxima written by the aggregation kernel for
+// gradients.  Weights are scaled per output row by the prep kernel.  Without a bound the 3xTF32 kernels run.
+constexpr int BK16 = 64;                             // 64 fp16 = 128 bytes = one swizzle atom row
+constexpr int UMMA_K16 = 16;                         // kind::f16
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// instruction descriptor for kind::f16 with fp16 inputs (a_format = b_format = 0), fp32 accumulate
+__host__ __device__ constexpr uint32_t make_idesc16(int M, int N, bool a_mn_major, bool b_mn_major) {
+    return (1u << 4) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) |
+           ((uint32_t)(M >> 4) << 24);
+}
+// bits of a non-negative float bound -> s = 2^(141-E) (s*bound < 2^15) and 1/s; E = biased exponent, clamped so that
+// both stay normal floats (an all-zero operand gets a huge but finite scale; inf/NaN propagate through s*x)
+__device__ __forceinline__ void scale_from_bits(uint32_t bits, float& s, float& inv_s) {
+    uint32_t E = (bits >> 23) & 0xFFu;
+    E = E < 16u ? 16u : (E > 252u ? 252u : E);
+    s = __uint_as_float((268u - E) << 23);
+    inv_s = __uint_as_float((E - 14u) << 23);
+}
+__device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(x0, x1);                     // x0 -> low half (lower address)
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+// 8 consecutive k values (already scaled) -> one 16-byte chunk of hi and one of lo
+__device__ __forceinline__ void split_f16x8(const float4& a, const float4& b, uint4& hi, uint4& lo) {
+    split_f16x2(a.x, a.y, hi.x, lo.x); split_f16x2(a.z, a.w, hi.y, lo.y);
+    split_f16x2(b.x, b.y, hi.z, lo.z); split_f16x2(b.z, b.w, hi.w, lo.w);
+}
+// max |arr[i]| over the whole CTA -> bits, via `slot` (shared, zeroed before the preceding __syncthreads)
+__device__ __forceinline__ void block_amax_bits(const float* __restrict__ arr, int64_t len, uint32_t* slot) {
+    uint32_t m = 0;
+    for (int64_t i = threadIdx.x; i < len; i += blockDim.x) {
+        const uint32_t b = __float_as_uint(fabsf(__ldg(arr + i)));
+        m = b > m ? b : m;
+    }
+    m = __reduce_max_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31) == 0) atomicMax(slot, m);                 // integer max: order-independent
+}
+
+struct Nt16Args {
+    const float* A;
+    const uint8_t* Bimg;     // fp16 hi/lo image of the scaled weights: [n_tile][k_block][hi|lo][BN rows x 128 B]
+    const float* inv_sw;     // [N] 1 / (scale of weight row n)
+    float* C;
+    const int* a_map;
+    const float* scale;
+    const float* shift;
+    float slope;
+    const float* amax;       // bound of |act(A)|: max over this array
+    int64_t amax_len;
+    int flags;               // bit 0: prefetch the next tile's A rows into L2
+    int64_t M;
+    int N, K;
+    int tiles_n;
+    int64_t num_tiles;
+};
+
+// A-operand producer of the fp16-split NT kernels: thread (row group t>>3, chunk c = t&7) handles 8 consecutive k of
+// NJ rows.  Loads first (so the wait for a free stage overlaps them), then transform + split + swizzled stores.
+template <int NJ, class Args>
+__device__ __forceinline__ void produce_load(const Args& g, const int64_t (&src_row)[NJ], int k0, float4 (&av)[NJ][2]) {
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        if (src_row[j] >= 0) {
+            av[j][0] = ldg4(g.A + src_row[j] * g.K + k0);
+            av[j][1] = ldg4(g.A + src_row[j] * g.K + k0 + 4);
+        } else {
+            av[j][0] = av[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+}
+template <int NJ, int RPP, class Args>
+__device__ __forceinline__ void produce_store(const Args& g, const int64_t (&src_row)[NJ], int k0, float4 (&av)[NJ][2],
+                                              float s_a, bool has_act, int t, uint32_t st, uint32_t a_bytes);
+// A k-block touches 256 bytes of each of the tile's 128 rows (stride K*4), and the next 256 bytes of the same rows a
+// microsecond later: DRAM sees short scattered bursts (measured: every shape of the fp16-split kernel ran at
+// ~3.6 TB/s of operand + result traffic).  Pulling the NEXT tile's rows into L2 as whole rows while the current tile
+// is multiplied makes the DRAM reads long and sequential and turns the producers' loads into L2 hits.
+template <class Args>
+__device__ __forceinline__ void prefetch_tile_l2(const Args& g, int64_t m0) {
+    const int t = threadIdx.x;
+    if (t >= BM) return;
+    const int64_t m = m0 + t;
+    if (m >= g.M) return;
+    const int64_t r = g.a_map ? (int64_t)__ldg(g.a_map + m) : m;
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(g.A + r * g.K), "r"((uint32_t)g.K * 4u) : "memory");
+}
+// The producer loop of a CTA.  (Issuing the loads one k-block further ahead from a second register buffer was
+// measured slower for both splits; so were L1::no_allocate loads: a thread's two 16-byte loads share a sector.)
+template <int STAGES, class Args, class WaitEmpty>
+__device__ __forceinline__ void produce_loop_simple(const Args& g, int64_t first_tile, int64_t tile_step, int64_t row_mul,
+                                                    int64_t row_add, int num_kb, float s_a, uint32_t smem_base,
+                                                    uint32_t stage_bytes, uint32_t a_bytes, uint64_t* full_bar,
+                                                    uint64_t* empty_bar, WaitEmpty wait_empty) {
+    constexpr int NJ = BM * 8 / kProducerThreads;
+    constexpr int RPP = kProducerThreads / 8;
+    const int t = threadIdx.x, lane = threadIdx.x & 31;
+    const int c8 = (t & 7) * 8;
+    const bool has_act = g.scale != nullptr;
+    uint32_t it = 0;
+    for (int64_t tile = first_tile; tile < g.num_tiles; tile += tile_step) {
+        const int64_t m0 = (tile / g.tiles_n) * row_mul + row_add;
+        if ((g.flags & 1) && tile + tile_step < g.num_tiles)
+            prefetch_tile_l2(g, ((tile + tile_step) / g.tiles_n) * row_mul + row_add);
+        int64_t src_row[NJ];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            const int64_t m = m0 + (t >> 3) + j * RPP;
+            src_row[j] = (m < g.M) ? (g.a_map ? (int64_t)__ldg(g.a_map + m) : m) : -1;
+        }
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1;
+            float4 av[NJ][2];
+            produce_load<NJ>(g, src_row, kb * BK16 + c8, av);
+            wait_empty(empty_bar + s, ph ^ 1u);
+            produce_store<NJ, RPP>(g, src_row, kb * BK16 + c8, av, s_a, has_act, t, smem_base + s * stage_bytes, a_bytes);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full_bar + s);
+        }
+    }
+}
+template <int NJ, int RPP, class Args>
+__device__ __forceinline__ void produce_store(const Args& g, const int64_t (&src_row)[NJ], int k0, float4 (&av)[NJ][2],
+                                              float s_a, bool has_act, int t, uint32_t st, uint32_t a_bytes) {
+    // the power-of-two operand scale is folded into the affine part (LeakyReLU is positively homogeneous)
+    float4 sc0 = make_float4(s_a, s_a, s_a, s_a), sc1 = sc0;
+    float4 sh0 = make_float4(0.f, 0.f, 0.f, 0.f), sh1 = sh0;
+    if (has_act) {
+        sc0 = ldg4(g.scale + k0); sc1 = ldg4(g.scale + k0 + 4);
+        sh0 = ldg4(g.shift + k0); sh1 = ldg4(g.shift + k0 + 4);
+        sc0.x *= s_a; sc0.y *= s_a; sc0.z *= s_a; sc0.w *= s_a; sc1.x *= s_a; sc1.y *= s_a; sc1.z *= s_a; sc1.w *= s_a;
+        sh0.x *= s_a; sh0.y *= s_a; sh0.z *= s_a; sh0.w *= s_a; sh1.x *= s_a; sh1.y *= s_a; sh1.z *= s_a; sh1.w *= s_a;
+    }
+    const uint32_t c = t & 7;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        const uint32_t row = (t >> 3) + j * RPP;
+        float4 a = av[j][0], b = av[j][1];
+        if (has_act) {
+            if (src_row[j] >= 0) {
+                a.x = lrelu_max(fmaf(a.x, sc0.x, sh0.x), g.slope); a.y = lrelu_max(fmaf(a.y, sc0.y, sh0.y), g.slope);
+                a.z = lrelu_max(fmaf(a.z, sc0.z, sh0.z), g.slope); a.w = lrelu_max(fmaf(a.w, sc0.w, sh0.w), g.slope);
+                b.x = lrelu_max(fmaf(b.x, sc1.x, sh1.x), g.slope); b.y = lrelu_max(fmaf(b.y, sc1.y, sh1.y), g.slope);
+                b.z = lrelu_max(fmaf(b.z, sc1.z, sh1.z), g.slope); b.w = lrelu_max(fmaf(b.w, sc1.w, sh1.w), g.slope);
+            }
+        } else {
+            a.x *= s_a; a.y *= s_a; a.z *= s_a; a.w *= s_a; b.x *= s_a; b.y *= s_a; b.z *= s_a; b.w *= s_a;
+        }
+        uint4 hi, lo;
+        split_f16x8(a, b, hi, lo);
+        const uint32_t off = sw128(row, c);
+        sts128(st + off, hi);
+        sts128(st + a_bytes + off, lo);
+    }
+}
+// epilogue of the fp16-split NT kernels: 32 columns of this thread's row, unscaled, through the swizzled staging tile
+template <class Args>
+__device__ __forceinline__ void epilogue_store32(const Args& g, uint32_t (&v)[32], float inv_sa, uint32_t stg, int lane,
+                                                 int64_t mrow0, int ncol0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {            // row = lane, 16-byte chunk i -> swizzled chunk i ^ (lane & 7)
+        const float4 w = ldg4(g.inv_sw + ncol0 + 4 * i);
+        uint4 o;
+        o.x = __float_as_uint(__uint_as_float(v[4 * i]) * inv_sa * w.x);
+        o.y = __float_as_uint(__uint_as_float(v[4 * i + 1]) * inv_sa * w.y);
+        o.z = __float_as_uint(__uint_as_float(v[4 * i + 2]) * inv_sa * w.z);
+        o.w = __float_as_uint(__uint_as_float(v[4 * i + 3]) * inv_sa * w.w);
+        sts128(stg + (uint32_t)lane * 128u + (uint32_t)((i ^ (lane & 7)) << 4), o);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int r = j * 4 + (lane >> 3), cc = lane & 7;
+        uint4 o;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w)
+                     : "r"(stg + (uint32_t)r * 128u + (uint32_t)((cc ^ (r & 7)) << 4)));
+        const int64_t m = mrow0 + r;
+        if (m < g.M) *reinterpret_cast<uint4*>(g.C + m * g.N + ncol0 + cc * 4) = o;
+    }
+    __syncwarp();
+}
+
+// W [N,K] (or, transposed, W^T given as [K,N]) -> per-row scaled fp16 hi/lo image; one warp per weight row n
+__global__ void tc_prep_b16_kernel(const float* __restrict__ W, int transposed, uint8_t* __restrict__ img,
+                                   float* __restrict__ inv_sw, int N, int K, int BN) {
+    const int n = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (n >= N) return;
+    const int chunks = K / 8;
+    auto load8 = [&](int c, float4& a, float4& b) {
+        const int k = c * 8;
+        if (!transposed) {
+            a = ldg4(W + (int64_t)n * K + k);
+            b = ldg4(W + (int64_t)n * K + k + 4);
+        } else {
+            a.x = __ldg(W + (int64_t)(k + 0) * N + n); a.y = __ldg(W + (int64_t)(k + 1) * N + n);
+            a.z = __ldg(W + (int64_t)(k + 2) * N + n); a.w = __ldg(W + (int64_t)(k + 3) * N + n);
+            b.x = __ldg(W + (int64_t)(k + 4) * N + n); b.y = __ldg(W + (int64_t)(k + 5) * N + n);
+            b.z = __ldg(W + (int64_t)(k + 6) * N + n); b.w = __ldg(W + (int64_t)(k + 7) * N + n);
+        }
+    };
+    uint32_t m = 0;
+    for (int c = lane; c < chunks; c += 32) {
+        float4 a, b;
+        load8(c, a, b);
+        const float mx = fmaxf(fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))),
+                               fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w))));
+        const uint32_t bits = __float_as_uint(mx);
+        m = bits > m ? bits : m;
+    }
+    m = __reduce_max_sync(0xffffffffu, m);
+    float s, inv_s;
+    scale_from_bits(m, s, inv_s);
+    if (lane == 0) inv_sw[n] = inv_s;
+    const int n_tile = n / BN, r = n % BN, num_kb = K / BK16;
+    const int64_t half_bytes = (int64_t)BN * 128;
+    for (int c = lane; c < chunks; c += 32) {
+        float4 a, b;
+        load8(c, a, b);
+        a.x *= s; a.y *= s; a.z *= s; a.w *= s; b.x *= s; b.y *= s; b.z *= s; b.w *= s;
+        uint4 hi, lo;
+        split_f16x8(a, b, hi, lo);
+        const int kb = c / 8, cc = c % 8;
+        const int64_t base = ((int64_t)n_tile * num_kb + kb) * 2 * half_bytes;
+        const uint32_t off = sw128((uint32_t)r, (uint32_t)cc);
+        *reinterpret_cast<uint4*>(img + base + off) = hi;
+        *reinterpret_cast<uint4*>(img + base + half_bytes + off) = lo;
+    }
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kV2Threads, 1) tc_gemm_nt16_kernel(const Nt16Args g) {
+    constexpr uint32_t A_BYTES = BM * 128;           // 128 rows x 64 fp16, one of hi / lo
+    constexpr uint32_t B_BYTES = BN * 128;
+    constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    constexpr uint32_t TMEM_COLS = 2 * BN;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* acc_full = empty_bar + STAGES;     // [2]
+    uint64_t* acc_empty = acc_full + 2;          // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    uint32_t* amax_slot = tmem_slot + 1;
+    uint8_t* staging = smem + STAGES * STAGE_BYTES + 256;   // 4 epilogue warps x 32 rows x 128 B
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_kb = g.K / BK16;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar + s, kProducerWarps + 1);
+            mbar_init(empty_bar + s, 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(acc_full + b, 1);
+            mbar_init(acc_empty + b, 4);
+        }
+        *amax_slot = 0u;
+        fence_barrier_init();
+    }
+    if (warp == 8) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    block_amax_bits(g.amax, g.amax_len, amax_slot);
+    __syncthreads();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t smem_base = smem_u32(smem);
+    float s_a, inv_sa;
+    scale_from_bits(*amax_slot, s_a, inv_sa);
+
+    if (warp < kProducerWarps) {
+        // ===== A producers (see produce_loop) =====
+        auto wait_empty = [](uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); };
+        produce_loop_simple<STAGES>(g, (int64_t)blockIdx.x, (int64_t)gridDim.x, (int64_t)BM, 0, num_kb, s_a,
+                                        smem_base, STAGE_BYTES, A_BYTES, full_bar, empty_bar, wait_empty);
+    } else if (warp == 8) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc16(BM, BN, false, false);
+            uint32_t it = 0, tile_no = 0;
+            for (int64_t tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++tile_no) {
+                const uint32_t buf = tile_no & 1u;
+                mbar_wait(acc_empty + buf, ((tile_no >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * BN;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(full_bar + s, ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + s * STAGE_BYTES;
+#pragma unroll
+                    for (int ks = 0; ks < BK16 / UMMA_K16; ++ks) {
+                        const uint32_t koff = ks * UMMA_K16 * 2;
+                        const uint64_t a_hi = make_desc(sa + koff, 16, 1024);
+                        const uint64_t a_lo = make_desc(sa + A_BYTES + koff, 16, 1024);
+                        const uint64_t b_hi = make_desc(sa + 2 * A_BYTES + koff, 16, 1024);
+                        const uint64_t b_lo = make_desc(sa + 2 * A_BYTES + B_BYTES + koff, 16, 1024);
+                        umma_f16(d_tmem, a_lo, b_hi, idesc, (kb | ks) != 0);
+                        umma_f16(d_tmem, a_hi, b_lo, idesc, 1);
+                        umma_f16(d_tmem, a_hi, b_hi, idesc, 1);
+                    }
+                    umma_commit(empty_bar + s);
+                }
+                umma_commit(acc_full + buf);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 9) {
+        // ===== B loader: one bulk copy per stage =====
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int64_t tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+                const int tn = (int)(tile % g.tiles_n);
+                const uint8_t* src = g.Bimg + (int64_t)tn * num_kb * (2 * (int64_t)B_BYTES);
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(empty_bar + s, ph ^ 1u);
+                    mbar_arrive_expect_tx(full_bar + s, 2 * B_BYTES);
+                    bulk_g2s(smem_base + s * STAGE_BYTES + 2 * A_BYTES, src + (int64_t)kb * (2 * (int64_t)B_BYTES),
+                             2 * B_BYTES, full_bar + s);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 12) {
+        // ===== epilogue: TMEM -> registers (unscale) -> swizzled staging tile -> global =====
+        const int q = warp & 3;
+        const uint32_t stg = smem_u32(staging) + (uint32_t)q * (32u * 128u);
+        uint32_t tile_no = 0;
+        for (int64_t tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++tile_no) {
+            const uint32_t buf = tile_no & 1u;
+            const int64_t mrow0 = (tile / g.tiles_n) * BM + q * 32;
+            const int n0 = (int)(tile % g.tiles_n) * BN;
+            mbar_wait(acc_full + buf, (tile_no >> 1) & 1u);
+            tc_fence_after();
+#pragma unroll 1
+            for (int cb = 0; cb < BN; cb += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)cb, v);
+                epilogue_store32(g, v, inv_sa, stg, lane, mrow0, n0 + cb);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty + buf);
+        }
+    }
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+template <int BN, int STAGES>
+static int launch_nt16(const Nt16Args& g, cudaStream_t st) {
+    constexpr size_t smem = (size_t)STAGES * (2 * BM * 128 + 2 * BN * 128) + 1024 + 256 + 4 * 32 * 128;
+    static bool configured = false;
+    if (!configured) {
+        DDMP_CUDA(cudaFuncSetAttribute(tc_gemm_nt16_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+        configured = true;
+    }
+    const int64_t grid = g.num_tiles < kNumSMs ? g.num_tiles : kNumSMs;
+    tc_gemm_nt16_kernel<BN, STAGES><<<(unsigned)grid, kV2Threads, smem, st>>>(g);
+    return check_launch("tc_gemm_nt16");
+}
+
+// fp16-split NT kernel on CTA pairs (cta_group::2, see tc_gemm_nt3_kernel for the synchronisation scheme): each CTA
+// stages its 128 rows of A and HALF of the weight tile, so the bytes a CTA pulls from L2 per k-block drop from 96 KB to
+// 64 KB (with the MMA time halved by kind::f16, the weight stream re-read for every row tile is what saturates the
+// SM's L2 port) and a third pipeline stage fits.
+__device__ __forceinline__ void umma_f16_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+constexpr int kNt16x2Stages = 3;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kV2Threads, 1) tc_gemm_nt16x2_kernel(const Nt16Args g) {
+    constexpr int STAGES = kNt16x2Stages;
+    constexpr int BN = 256;
+    constexpr uint32_t A_BYTES = BM * 128;
+    constexpr uint32_t B_HALF = (BN / 2) * 128;          // this CTA's half of the weight tile, one of hi / lo
+    constexpr uint32_t B_FULL = BN * 128;
+    constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_HALF;
+    constexpr uint32_t TMEM_COLS = 2 * BN;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* peer_ready = empty_bar + STAGES;
+    uint64_t* acc_full = peer_ready + STAGES;
+    uint64_t* acc_empty = acc_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    uint32_t* amax_slot = tmem_slot + 1;
+    uint8_t* staging = smem + STAGES * STAGE_BYTES + 256;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int num_kb = g.K / BK16;
+    const int64_t num_pairs = gridDim.x / 2, pair = blockIdx.x / 2;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar + s, kProducerWarps + 1);
+            mbar_init(empty_bar + s, 1);
+            mbar_init(peer_ready + s, 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(acc_full + b, 1);
+            mbar_init(acc_empty + b, 8);
+        }
+        *amax_slot = 0u;
+        fence_barrier_init();
+    }
+    cluster_sync_all();
+    if (warp == 8) tmem_alloc_2cta(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    block_amax_bits(g.amax, g.amax_len, amax_slot);
+    __syncthreads();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t smem_base = smem_u32(smem);
+    float s_a, inv_sa;
+    scale_from_bits(*amax_slot, s_a, inv_sa);
+
+    if (warp < kProducerWarps) {
+        auto wait_empty = [](uint64_t* bar, uint32_t parity) { mbar_wait_cluster(bar, parity); };
+        produce_loop_simple<STAGES>(g, pair, num_pairs, (int64_t)(2 * BM), (int64_t)rank * BM, num_kb, s_a,
+                                        smem_base, STAGE_BYTES, A_BYTES, full_bar, empty_bar, wait_empty);
+    } else if (warp == 8) {
+        if (lane == 0) {
+            uint32_t it = 0, tile_no = 0;
+            if (rank == 0) {
+                constexpr uint32_t idesc = make_idesc16(2 * BM, BN, false, false);
+                for (int64_t tile = pair; tile < g.num_tiles; tile += num_pairs, ++tile_no) {
+                    const uint32_t buf = tile_no & 1u;
+                    mbar_wait_cluster(acc_empty + buf, ((tile_no >> 1) & 1u) ^ 1u);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + buf * BN;
+                    for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                        const int s = it % STAGES;
+                        const uint32_t ph = (it / STAGES) & 1;
+                        mbar_wait(full_bar + s, ph);
+                        mbar_wait_cluster(peer_ready + s, ph);
+                        tc_fence_after();
+                        const uint32_t sa = smem_base + s * STAGE_BYTES;
+#pragma unroll
+                        for (int ks = 0; ks < BK16 / UMMA_K16; ++ks) {
+                            const uint32_t koff = ks * UMMA_K16 * 2;
+                            const uint64_t a_hi = make_desc(sa + koff, 16, 1024);
+                            const uint64_t a_lo = make_desc(sa + A_BYTES + koff, 16, 1024);
+                            const uint64_t b_hi = make_desc(sa + 2 * A_BYTES + koff, 16, 1024);
+                            const uint64_t b_lo = make_desc(sa + 2 * A_BYTES + B_HALF + koff, 16, 1024);
+                            umma_f16_2cta(d_tmem, a_lo, b_hi, idesc, (kb | ks) != 0);
+                            umma_f16_2cta(d_tmem, a_hi, b_lo, idesc, 1);
+                            umma_f16_2cta(d_tmem, a_hi, b_hi, idesc, 1);
+                        }
+                        umma_commit_2cta(empty_bar + s);
+                    }
+                    umma_commit_2cta(acc_full + buf);
+                }
+            } else {
+                for (int64_t tile = pair; tile < g.num_tiles; tile += num_pairs) {
+                    for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                        const int s = it % STAGES;
+                        const uint32_t ph = (it / STAGES) & 1;
+                        mbar_wait(full_bar + s, ph);
+                        mbar_arrive_remote(peer_ready + s, 0);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 9) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int64_t tile = pair; tile < g.num_tiles; tile += num_pairs) {
+                const int tn = (int)(tile % g.tiles_n);
+                const uint8_t* src = g.Bimg + (int64_t)tn * num_kb * (2 * (int64_t)B_FULL) + (int64_t)rank * B_HALF;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait_cluster(empty_bar + s, ph ^ 1u);
+                    mbar_arrive_expect_tx(full_bar + s, 2 * B_HALF);
+                    const uint8_t* sk = src + (int64_t)kb * (2 * (int64_t)B_FULL);
+                    const uint32_t dst = smem_base + s * STAGE_BYTES + 2 * A_BYTES;
+                    bulk_g2s(dst, sk, B_HALF, full_bar + s);
+                    bulk_g2s(dst + B_HALF, sk + B_FULL, B_HALF, full_bar + s);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 12) {
+        const int q = warp & 3;
+        const uint32_t stg = smem_u32(staging) + (uint32_t)q * (32u * 128u);
+        uint32_t tile_no = 0;
+        for (int64_t tile = pair; tile < g.num_tiles; tile += num_pairs, ++tile_no) {
+            const uint32_t buf = tile_no & 1u;
+            const int64_t mrow0 = (tile / g.tiles_n) * (2 * BM) + rank * BM + q * 32;
+            const int n0 = (int)(tile % g.tiles_n) * BN;
+            mbar_wait_cluster(acc_full + buf, (tile_no >> 1) & 1u);
+            tc_fence_after();
+#pragma unroll 1
+            for (int cb = 0; cb < BN; cb += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)cb, v);
+                epilogue_store32(g, v, inv_sa, stg, lane, mrow0, n0 + cb);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (rank == 0) mbar_arrive(acc_empty + buf);
+                else mbar_arrive_remote(acc_empty + buf, 0);
+            }
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 8) {
+        tc_fence_after();
+        tmem_dealloc_2cta(tmem_base, TMEM_COLS);
+    }
+}
+
+static int launch_nt16x2(const Nt16Args& g0, cudaStream_t st) {
+    constexpr size_t smem = (size_t)kNt16x2Stages * (2 * BM * 128 + 2 * 128 * 128) + 1024 + 256 + 4 * 32 * 128;
+    static bool configured = false;
+    if (!configured) {
+        DDMP_CUDA(cudaFuncSetAttribute(tc_gemm_nt16x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    Nt16Args g = g0;
+    g.num_tiles = ceil_div(g.M, 2 * BM) * g.tiles_n;
+    const int64_t pairs = g.num_tiles < kNumSMs / 2 ? g.num_tiles : kNumSMs / 2;
+    tc_gemm_nt16x2_kernel<<<(unsigned)(2 * pairs), kV2Threads, smem, st>>>(g);
+    return check_launch("tc_gemm_nt16x2");
+}
+
+static bool f16_split_enabled() {
+    static const bool v = [] { const char* e = getenv("DDMP_TC_SPLIT"); return !(e && e[0] == 't'); }();   // "tf32"
+    return v;
+}
+
+static int run_nt16(const float* A, const int* a_map, const float* scale, const float* shift, float slope,
+                    const float* W, int transposed, void* workspace, float* C, int64_t M, int N, int K,
+                    const float* amax, int64_t amax_len, cudaStream_t st) {
+    const int BN = (N % 256 == 0) ? 256 : ((N % 128 == 0) ? 128 : 64);
+    uint8_t* img = reinterpret_cast<uint8_t*>(workspace);
+    float* inv_sw = reinterpret_cast<float*>(img + (int64_t)N * K * 4);          // after the hi + lo images
+    tc_prep_b16_kernel<<<(unsigned)ceil_div((int64_t)N * 32, 256), 256, 0, st>>>(W, transposed, img, inv_sw, N, K, BN);
+    int rc = check_launch("tc_prep_b16");
+    if (rc) return rc;
+    Nt16Args g{};
+    g.A = A; g.Bimg = img; g.inv_sw = inv_sw; g.C = C; g.a_map = a_map; g.scale = scale; g.shift = shift;
+    g.slope = slope; g.amax = amax; g.amax_len = amax_len;
+    static const int flags = [] { const char* e = getenv("DDMP_TC_F16_FLAGS"); return e ? atoi(e) : 0; }();
+    g.flags = flags;
+    g.M = M; g.N = N; g.K = K; g.tiles_n = N / BN;
+    g.num_tiles = ceil_div(M, BM) * g.tiles_n;
+    DDMP_REQUIRE(g.num_tiles < (1ll << 31), "tc gemm: too many tiles");
+    static const bool one_cta = [] { const char* e = getenv("DDMP_TC_2CTA"); return e && e[0] == '0'; }();
+    if (BN == 256 && !one_cta) return launch_nt16x2(g, st);
+    if (BN == 256) return launch_nt16<256, 2>(g, st);
+    if (BN == 128) return launch_nt16<128, 3>(g, st);
+    return launch_nt16<64, 4>(g, st);
+}
+
 // ---- TN kernel (dW) -------------------------------------------------------------------------------------------------
 // dW[M=Cout, N=Cin] = sum over rows r of A[r, m] * act(B)[r, n].  Both operands are MN-major: a K index is a graph
 // row, and a row of dH / X is contiguous along the channel.  SWIZZLE_128B MN-major canonical layout (CUTLASS
@@ -1221,6 +1825,249 @@ static int launch_tn(const TnArgs& g, cudaStream_t st) {
     return launch_tn_impl<BN, STAGES, 8>(g, st);
 }
 
+// ---- TN kernel (dW), fp16 split --------------------------------------------------------------------------------------
+// Same work decomposition as tc_gemm_tn_kernel (row segments x output tiles, float64 segment reduction); operands are
+// scaled by powers of two from their bounds (`amax_a`: row-block maxima of dH from the aggregation kernel, `amax_b`:
+// the BatchNorm bound of act(X)), split into fp16 hi/lo and stored MN-major in the 16-bit SWIZZLE_128B canonical
+// layout: element (mn, k) of a stage at
+//     (mn/64)*LBO + (k/8)*1024 + (k%8)*128 + ((((mn%64)/8) ^ (k%8)) * 16) + (mn%8)*2,    LBO = (BK16/8)*1024
+// i.e. a k-row (one graph row) of 64 channels is one 128-byte line, exactly how it lies in global memory.
+struct Tn16Args {
+    const float* A;       // dH [rows, M] row-major
+    const float* B;       // X  [rows, N] row-major (pre-BatchNorm), act over n when scale != null
+    float* P;             // partials [num_seg][M][N]
+    const float* scale;
+    const float* shift;
+    float slope;
+    const float* amax_a;
+    int64_t amax_a_len;
+    const float* amax_b;
+    int64_t amax_b_len;
+    int64_t rows;
+    int M, N;
+    int tiles_m, tiles_n;
+    int64_t num_items;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(16 * 32 + 32, 1) tc_gemm_tn16_kernel(const Tn16Args g) {
+    constexpr int PW = 16;
+    constexpr int kPT = PW * 32;
+    constexpr uint32_t A_BYTES = BM * BK16 * 2;      // 64 k-rows x 128 m x 2 B
+    constexpr uint32_t B_BYTES = BN * BK16 * 2;
+    constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+    constexpr uint32_t LBO = (BK16 / 8) * 1024;      // next 64-wide MN block
+    constexpr uint32_t SBO = 1024;                   // next group of 8 k-rows
+    constexpr int A_CH = BM / 8, B_CH = BN / 8;      // 16-byte chunks (8 channels) per k-row
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* accum_bar = empty_bar + STAGES;
+    uint64_t* drained_bar = accum_bar + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(drained_bar + 1);
+    uint32_t* amax_slot = tmem_slot + 1;             // [2]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar + s, PW);
+            mbar_init(empty_bar + s, 1);
+        }
+        mbar_init(accum_bar, 1);
+        mbar_init(drained_bar, PW);
+        amax_slot[0] = 0u;
+        amax_slot[1] = 0u;
+        fence_barrier_init();
+    }
+    if (warp == PW) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    block_amax_bits(g.amax_a, g.amax_a_len, amax_slot);
+    block_amax_bits(g.amax_b, g.amax_b_len, amax_slot + 1);
+    __syncthreads();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t smem_base = smem_u32(smem);
+    float s_a, inv_sa, s_b, inv_sb;
+    scale_from_bits(amax_slot[0], s_a, inv_sa);
+    scale_from_bits(amax_slot[1], s_b, inv_sb);
+    const int tiles = g.tiles_m * g.tiles_n;
+
+    uint32_t it = 0;
+    uint32_t item_no = 0;
+    for (int64_t item = blockIdx.x; item < g.num_items; item += gridDim.x, ++item_no) {
+        const int tile = (int)(item % tiles);
+        const int64_t seg = item / tiles;
+        const int m0 = (tile / g.tiles_n) * BM, n0 = (tile % g.tiles_n) * BN;
+        const int64_t r0 = seg * kSegRows;
+        const int64_t r1 = (r0 + kSegRows < g.rows) ? (r0 + kSegRows) : g.rows;
+        const int num_kb = (int)((r1 - r0 + BK16 - 1) / BK16);
+
+        if (warp < PW) {
+            const int t = threadIdx.x;
+            const uint32_t a_cm = t % A_CH, a_r = t / A_CH;
+            const uint32_t b_cm = t % B_CH, b_r = t / B_CH;
+            constexpr int A_PASS = kPT / A_CH, B_PASS = kPT / B_CH;            // k-rows per pass of the producers
+            constexpr int A_N = BK16 / A_PASS, B_N = BK16 / B_PASS;
+            const bool a_ok = (m0 + (int)a_cm * 8) < g.M;
+            const bool has_act = g.scale != nullptr;
+            float4 sc0 = make_float4(s_b, s_b, s_b, s_b), sc1 = sc0;
+            float4 sh0 = make_float4(0.f, 0.f, 0.f, 0.f), sh1 = sh0;
+            if (has_act) {
+                sc0 = ldg4(g.scale + n0 + b_cm * 8); sc1 = ldg4(g.scale + n0 + b_cm * 8 + 4);
+                sh0 = ldg4(g.shift + n0 + b_cm * 8); sh1 = ldg4(g.shift + n0 + b_cm * 8 + 4);
+                sc0.x *= s_b; sc0.y *= s_b; sc0.z *= s_b; sc0.w *= s_b; sc1.x *= s_b; sc1.y *= s_b; sc1.z *= s_b; sc1.w *= s_b;
+                sh0.x *= s_b; sh0.y *= s_b; sh0.z *= s_b; sh0.w *= s_b; sh1.x *= s_b; sh1.y *= s_b; sh1.z *= s_b; sh1.w *= s_b;
+            }
+            const uint32_t a_off0 = (a_cm / 8) * LBO, b_off0 = (b_cm / 8) * LBO;
+            const uint32_t a_cj = a_cm & 7u, b_cj = b_cm & 7u;
+            float4 av[A_N][2], bv[B_N][2];
+            auto issue = [&](int kb) {
+                if (kb >= num_kb) return;
+                const int64_t rb = r0 + (int64_t)kb * BK16;
+#pragma unroll
+                for (int j = 0; j < A_N; ++j) {
+                    const int64_t r = rb + a_r + j * A_PASS;
+                    if (r < r1 && a_ok) {
+                        av[j][0] = ldg4(g.A + r * g.M + m0 + a_cm * 8);
+                        av[j][1] = ldg4(g.A + r * g.M + m0 + a_cm * 8 + 4);
+                    } else {
+                        av[j][0] = av[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < B_N; ++j) {
+                    const int64_t r = rb + b_r + j * B_PASS;
+                    if (r < r1) {
+                        bv[j][0] = ldg4(g.B + r * g.N + n0 + b_cm * 8);
+                        bv[j][1] = ldg4(g.B + r * g.N + n0 + b_cm * 8 + 4);
+                    } else {
+                        bv[j][0] = bv[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+            };
+            issue(0);
+            for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                const int64_t rb = r0 + (int64_t)kb * BK16;
+                mbar_wait(empty_bar + s, ph ^ 1u);
+                const uint32_t st = smem_base + s * STAGE_BYTES;
+#pragma unroll
+                for (int j = 0; j < A_N; ++j) {
+                    const uint32_t k = a_r + j * A_PASS;
+                    float4 a = av[j][0], b = av[j][1];
+                    a.x *= s_a; a.y *= s_a; a.z *= s_a; a.w *= s_a; b.x *= s_a; b.y *= s_a; b.z *= s_a; b.w *= s_a;
+                    uint4 hi, lo;
+                    split_f16x8(a, b, hi, lo);
+                    const uint32_t off = a_off0 + (k >> 3) * SBO + (k & 7u) * 128u + ((a_cj ^ (k & 7u)) << 4);
+                    sts128(st + off, hi);
+                    sts128(st + A_BYTES + off, lo);
+                }
+#pragma unroll
+                for (int j = 0; j < B_N; ++j) {
+                    const uint32_t k = b_r + j * B_PASS;
+                    float4 a = bv[j][0], b = bv[j][1];
+                    if (has_act) {
+                        if ((rb + k) < r1) {
+                            a.x = lrelu_max(fmaf(a.x, sc0.x, sh0.x), g.slope); a.y = lrelu_max(fmaf(a.y, sc0.y, sh0.y), g.slope);
+                            a.z = lrelu_max(fmaf(a.z, sc0.z, sh0.z), g.slope); a.w = lrelu_max(fmaf(a.w, sc0.w, sh0.w), g.slope);
+                            b.x = lrelu_max(fmaf(b.x, sc1.x, sh1.x), g.slope); b.y = lrelu_max(fmaf(b.y, sc1.y, sh1.y), g.slope);
+                            b.z = lrelu_max(fmaf(b.z, sc1.z, sh1.z), g.slope); b.w = lrelu_max(fmaf(b.w, sc1.w, sh1.w), g.slope);
+                        }
+                    } else {
+                        a.x *= s_b; a.y *= s_b; a.z *= s_b; a.w *= s_b; b.x *= s_b; b.y *= s_b; b.z *= s_b; b.w *= s_b;
+                    }
+                    uint4 hi, lo;
+                    split_f16x8(a, b, hi, lo);
+                    const uint32_t off = b_off0 + (k >> 3) * SBO + (k & 7u) * 128u + ((b_cj ^ (k & 7u)) << 4);
+                    sts128(st + 2 * A_BYTES + off, hi);
+                    sts128(st + 2 * A_BYTES + B_BYTES + off, lo);
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full_bar + s);
+                issue(kb + 1);
+            }
+            // ---- epilogue of this item ----
+            mbar_wait(accum_bar, item_no & 1u);
+            tc_fence_after();
+            constexpr int PARTS = PW / 4;
+            constexpr int CPART = (BN / PARTS) < 32 ? 32 : (BN / PARTS);
+            const int q = warp & 3, part = warp >> 2;
+            const int m = m0 + q * 32 + lane;
+            float* prow = g.P + (seg * g.M + m) * (int64_t)g.N + n0;
+            const float inv = inv_sa * inv_sb;       // both are normal powers of two well inside the float range
+#pragma unroll 1
+            for (int cb = part * CPART; cb < (part + 1) * CPART && cb < BN; cb += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, v);
+                if (m < g.M) {
+#pragma unroll
+                    for (int e = 0; e < 32; e += 4)
+                        st4(prow + cb + e, make_float4(__uint_as_float(v[e]) * inv, __uint_as_float(v[e + 1]) * inv,
+                                                       __uint_as_float(v[e + 2]) * inv, __uint_as_float(v[e + 3]) * inv));
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(drained_bar);
+        } else {
+            if (lane == 0) {
+                constexpr uint32_t idesc = make_idesc16(BM, BN, true, true);
+                if (item_no > 0) {
+                    mbar_wait(drained_bar, (item_no - 1) & 1u);
+                    tc_fence_after();
+                }
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(full_bar + s, ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+#pragma unroll
+                    for (int ks = 0; ks < BK16 / UMMA_K16; ++ks) {
+                        const uint32_t koff = ks * 2u * SBO;                    // 16 k-rows = two 8-row groups
+                        const uint64_t a_hi = make_desc(sa + koff, LBO, SBO, 2);
+                        const uint64_t a_lo = make_desc(sa + A_BYTES + koff, LBO, SBO, 2);
+                        const uint64_t b_hi = make_desc(sa + 2 * A_BYTES + koff, LBO, SBO, 2);
+                        const uint64_t b_lo = make_desc(sa + 2 * A_BYTES + B_BYTES + koff, LBO, SBO, 2);
+                        umma_f16(tmem_base, a_lo, b_hi, idesc, (kb | ks) != 0);
+                        umma_f16(tmem_base, a_hi, b_lo, idesc, 1);
+                        umma_f16(tmem_base, a_hi, b_hi, idesc, 1);
+                    }
+                    umma_commit(empty_bar + s);
+                }
+                umma_commit(accum_bar);
+            } else {
+                it += num_kb;
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    if (warp == PW) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+template <int BN, int STAGES>
+static int launch_tn16(const Tn16Args& g, cudaStream_t st) {
+    constexpr size_t smem = (size_t)STAGES * (2 * BM * BK16 * 2 + 2 * BN * BK16 * 2) + 1024 + 256;
+    static bool configured = false;
+    if (!configured) {
+        DDMP_CUDA(cudaFuncSetAttribute(tc_gemm_tn16_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+        configured = true;
+    }
+    const int64_t grid = g.num_items < kNumSMs ? g.num_items : kNumSMs;
+    tc_gemm_tn16_kernel<BN, STAGES><<<(unsigned)grid, 16 * 32 + 32, smem, st>>>(g);
+    return check_launch("tc_gemm_tn16");
+}
+
 __global__ void transpose_kernel(const float* __restrict__ W, float* __restrict__ Wt, int rows, int cols) {
     __shared__ float tile[32][33];
     const int x = blockIdx.x * 32 + threadIdx.x, y0 = blockIdx.y * 32;
@@ -1255,17 +2102,19 @@ static bool use_v1() {
 
 int tc_gemm_xw(const float* X, const int32_t* row_map, const float* scale, const float* shift, float slope,
                const float* W, float* H, void* workspace, int64_t workspace_bytes, int64_t n, int32_t Cin,
-               int32_t Cout, cudaStream_t st) {
+               int32_t Cout, const float* amax, int64_t amax_len, cudaStream_t st) {
     DDMP_REQUIRE(tc_aligned16(X) && tc_aligned16(W) && tc_aligned16(H), "tc_gemm_xw: pointers must be 16-byte aligned");
     if (use_v1()) return tc::run_nt(X, row_map, scale, shift, slope, W, H, n, Cout, Cin, st);
     DDMP_REQUIRE(workspace && tc_aligned16(workspace) && workspace_bytes >= tc_gemm_nt_workspace_bytes(Cin, Cout),
                  "tc_gemm_xw: workspace too small");
+    if (amax && amax_len > 0 && Cin % tc::BK16 == 0 && tc::f16_split_enabled())
+        return tc::run_nt16(X, row_map, scale, shift, slope, W, 0, workspace, H, n, Cout, Cin, amax, amax_len, st);
     return tc::run_nt2(X, row_map, scale, shift, slope, W, 0, workspace, H, n, Cout, Cin, st);
 }
 
 // gX[n,Cin] = dH[n,Cout] * W[Cout,Cin]: B operand (K-major) is W^T, built directly into the swizzled image.
 int tc_gemm_dx(const float* dH, const float* W, float* gX, void* workspace, int64_t workspace_bytes, int64_t n,
-               int32_t Cin, int32_t Cout, cudaStream_t st) {
+               int32_t Cin, int32_t Cout, const float* amax, int64_t amax_len, cudaStream_t st) {
     DDMP_REQUIRE(tc_aligned16(dH) && tc_aligned16(W) && tc_aligned16(gX), "tc_gemm_dx: pointers must be 16-byte aligned");
     DDMP_REQUIRE(workspace && tc_aligned16(workspace) && workspace_bytes >= tc_gemm_nt_workspace_bytes(Cin, Cout),
                  "tc_gemm_dx: workspace too small");
@@ -1277,6 +2126,8 @@ int tc_gemm_dx(const float* dH, const float* W, float* gX, void* workspace, int6
         if (rc) return rc;
         return tc::run_nt(dH, nullptr, nullptr, nullptr, 0.f, wt, gX, n, Cin, Cout, st);
     }
+    if (amax && amax_len > 0 && Cout % tc::BK16 == 0 && tc::f16_split_enabled())
+        return tc::run_nt16(dH, nullptr, nullptr, nullptr, 0.f, W, 1, workspace, gX, n, Cin, Cout, amax, amax_len, st);
     return tc::run_nt2(dH, nullptr, nullptr, nullptr, 0.f, W, 1, workspace, gX, n, Cin, Cout, st);
 }
 
@@ -1286,11 +2137,32 @@ int64_t tc_gemm_dw_workspace_bytes(int64_t n, int32_t Cin, int32_t Cout) {
 
 int tc_gemm_dw(const float* dH, const float* X, const int32_t* row_map, const float* scale, const float* shift,
                float slope, float* dW, void* workspace, int64_t workspace_bytes, int64_t n, int32_t Cin, int32_t Cout,
-               cudaStream_t st) {
+               const float* amax_dh, int64_t amax_dh_len, const float* amax_x, int64_t amax_x_len, cudaStream_t st) {
     DDMP_REQUIRE(row_map == nullptr, "tc_gemm_dw: row_map is only supported by the FFMA path");
     DDMP_REQUIRE(workspace && workspace_bytes >= tc_gemm_dw_workspace_bytes(n, Cin, Cout),
                  "tc_gemm_dw: workspace too small (%lld bytes)", (long long)workspace_bytes);
     DDMP_REQUIRE(tc_aligned16(dH) && tc_aligned16(X) && tc_aligned16(workspace), "tc_gemm_dw: 16-byte alignment");
+    const int64_t count = (int64_t)Cin * Cout;
+    // both operands are split by the producer warps here, which bounds this kernel: the fp16 split only pays for
+    // the narrow inputs (measured, 1M rows: 64->128 0.26 vs 0.36 ms, 128->256 0.46 vs 0.62, but 256->256 0.88 vs
+    // 0.79 and 512->512 2.93 vs 2.71); DDMP_TC_TN16=1 forces it everywhere
+    static const bool tn16_all = [] { const char* e = getenv("DDMP_TC_TN16"); return e && e[0] == '1'; }();
+    if (amax_dh && amax_x && amax_dh_len > 0 && amax_x_len > 0 && Cout % 8 == 0 && tc::f16_split_enabled() &&
+        (Cin <= 128 || tn16_all)) {
+        tc::Tn16Args h{};
+        h.A = dH; h.B = X; h.P = reinterpret_cast<float*>(workspace); h.scale = scale; h.shift = shift; h.slope = slope;
+        h.amax_a = amax_dh; h.amax_a_len = amax_dh_len; h.amax_b = amax_x; h.amax_b_len = amax_x_len;
+        h.rows = n; h.M = Cout; h.N = Cin;
+        h.tiles_m = (int)ceil_div(Cout, tc::BM);
+        const int64_t segs16 = ceil_div(n, tc::kSegRows);
+        int rc16;
+        if (Cin % 256 == 0) { h.tiles_n = Cin / 256; h.num_items = segs16 * h.tiles_m * h.tiles_n; rc16 = tc::launch_tn16<256, 2>(h, st); }
+        else if (Cin % 128 == 0) { h.tiles_n = Cin / 128; h.num_items = segs16 * h.tiles_m * h.tiles_n; rc16 = tc::launch_tn16<128, 3>(h, st); }
+        else { h.tiles_n = Cin / 64; h.num_items = segs16 * h.tiles_m * h.tiles_n; rc16 = tc::launch_tn16<64, 4>(h, st); }
+        if (rc16) return rc16;
+        tc::seg_reduce_kernel<<<(unsigned)ceil_div(count, 256), 256, 0, st>>>(h.P, dW, count, segs16);
+        return check_launch("tc seg_reduce");
+    }
     tc::TnArgs g{};
     g.A = dH; g.B = X; g.P = reinterpret_cast<float*>(workspace); g.scale = scale; g.shift = shift; g.slope = slope;
     g.rows = n; g.M = Cout; g.N = Cin;
@@ -1301,7 +2173,6 @@ int tc_gemm_dw(const float* dH, const float* X, const int32_t* row_map, const fl
     else if (Cin % 128 == 0) { g.tiles_n = Cin / 128; g.num_items = segs * g.tiles_m * g.tiles_n; rc = tc::launch_tn<128, 3>(g, st); }
     else { g.tiles_n = Cin / 64; g.num_items = segs * g.tiles_m * g.tiles_n; rc = tc::launch_tn<64, 4>(g, st); }
     if (rc) return rc;
-    const int64_t count = (int64_t)Cin * Cout;
     tc::seg_reduce_kernel<<<(unsigned)ceil_div(count, 256), 256, 0, st>>>(g.P, dW, count, segs);
     return check_launch("tc seg_reduce");
 }

@@ -18,7 +18,8 @@ template <int C, bool STATS, bool BIAS>
 __global__ void __launch_bounds__(256, (STATS || C >= 512) ? 3 : 4)
 spmm_gcn_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const float* __restrict__ w,
                 const float* __restrict__ H, const float* __restrict__ bias, float* __restrict__ Y,
-                float* __restrict__ partials, int64_t n, int rows_per_block, int blocks_per_cta) {
+                float* __restrict__ partials, float* __restrict__ amax_blocks, int64_t n, int rows_per_block,
+                int blocks_per_cta) {
     constexpr int G = (C / 4 < 32) ? (C / 4) : 32;
     constexpr int NV = C / (4 * G);
     constexpr int GROUPS = 256 / G;
@@ -37,6 +38,7 @@ spmm_gcn_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, con
     // BatchNorm partial sums live in shared memory, one private [2][C] slice per row group (keeping them in
     // registers costs 8*NV registers and halves the occupancy of the widest instantiation: ncu, profiles/)
     __shared__ __align__(16) float red[STATS ? GROUPS * 2 * C : 4];
+    __shared__ float wmax[8];
     float* myred = red + gid * 2 * C;
     // A CTA walks `blocks_per_cta` consecutive row blocks (1 by default, see launch_spmm).
     const int64_t nblk = (n + rows_per_block - 1) / rows_per_block;
@@ -45,6 +47,7 @@ spmm_gcn_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, con
     for (int64_t blk = blk_begin; blk < blk_end; ++blk) {
     const int64_t row0 = blk * rows_per_block;
     const int64_t row_end = (row0 + rows_per_block < n) ? (row0 + rows_per_block) : n;
+    float amx = 0.f;                                 // max |Y| over this thread's outputs of the row block
     if (STATS) {
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
@@ -141,6 +144,7 @@ spmm_gcn_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, con
                 o.x += bsum[v].x; o.y += bsum[v].y; o.z += bsum[v].z; o.w += bsum[v].w;
             }
             st4(yp + (v * G + lg) * 4, o);
+            amx = fmaxf(fmaxf(amx, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
             if (STATS) {
                 float4 s = *reinterpret_cast<float4*>(myred + (v * G + lg) * 4);
                 float4 q = *reinterpret_cast<float4*>(myred + C + (v * G + lg) * 4);
@@ -163,6 +167,19 @@ spmm_gcn_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, con
 #pragma unroll 8
             for (int g = 0; g < GROUPS; ++g) t += red[g * 2 * C + i];
             outp[i] = t;
+        }
+        __syncthreads();
+    }
+    if (amax_blocks) {                               // operand bound for the fp16-split GEMMs that consume Y
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) amx = fmaxf(amx, __shfl_xor_sync(0xffffffffu, amx, o));
+        if (lane == 0) wmax[threadIdx.x >> 5] = amx;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float m = wmax[0];
+#pragma unroll
+            for (int i = 1; i < 8; ++i) m = fmaxf(m, wmax[i]);
+            amax_blocks[blk] = m;
         }
         __syncthreads();
     }
@@ -337,7 +354,7 @@ __global__ void gcn_edge_weights_kernel(const int* __restrict__ rowptr, const in
 
 template <int C>
 static int launch_spmm(const int* rowptr, const int* col, const float* w, const float* H, const float* bias,
-                       float* Y, float* partials, int64_t n, cudaStream_t st) {
+                       float* Y, float* partials, float* amax_blocks, int64_t n, cudaStream_t st) {
     const int rpb = ddmp_rows_per_block(C);
     const int64_t nblk = ceil_div(n, rpb);
     // consecutive row blocks per CTA (DDMP_SPMM_CHUNK).  Default 1: walking 4 or 8 neighbouring blocks per CTA to
@@ -348,11 +365,11 @@ static int launch_spmm(const int* rowptr, const int* col, const float* w, const 
     while (bpc > 1 && ceil_div(nblk, bpc) < 8 * kNumSMs) --bpc;
     const unsigned grid = (unsigned)ceil_div(nblk, bpc);
     if (partials) {
-        if (bias) spmm_gcn_kernel<C, true, true><<<grid, 256, 0, st>>>(rowptr, col, w, H, bias, Y, partials, n, rpb, bpc);
-        else spmm_gcn_kernel<C, true, false><<<grid, 256, 0, st>>>(rowptr, col, w, H, bias, Y, partials, n, rpb, bpc);
+        if (bias) spmm_gcn_kernel<C, true, true><<<grid, 256, 0, st>>>(rowptr, col, w, H, bias, Y, partials, amax_blocks, n, rpb, bpc);
+        else spmm_gcn_kernel<C, true, false><<<grid, 256, 0, st>>>(rowptr, col, w, H, bias, Y, partials, amax_blocks, n, rpb, bpc);
     } else {
-        if (bias) spmm_gcn_kernel<C, false, true><<<grid, 256, 0, st>>>(rowptr, col, w, H, bias, Y, partials, n, rpb, bpc);
-        else spmm_gcn_kernel<C, false, false><<<grid, 256, 0, st>>>(rowptr, col, w, H, bias, Y, partials, n, rpb, bpc);
+        if (bias) spmm_gcn_kernel<C, false, true><<<grid, 256, 0, st>>>(rowptr, col, w, H, bias, Y, partials, amax_blocks, n, rpb, bpc);
+        else spmm_gcn_kernel<C, false, false><<<grid, 256, 0, st>>>(rowptr, col, w, H, bias, Y, partials, amax_blocks, n, rpb, bpc);
     }
     return check_launch("spmm_gcn");
 }
@@ -369,22 +386,22 @@ int ddmp_gcn_edge_weights(const int32_t* rowptr, const int32_t* col, float* w, i
 }
 
 int ddmp_spmm_gcn(const int32_t* rowptr, const int32_t* col, const float* w, const float* H, const float* bias,
-                  float* Y, float* stats_partials, int64_t n, int32_t C, void* stream) {
+                  float* Y, float* stats_partials, float* amax_blocks, int64_t n, int32_t C, void* stream) {
     using namespace ddmp;
     DDMP_REQUIRE(n >= 0 && C > 0, "spmm_gcn: bad shape n=%lld C=%d", (long long)n, C);
     if (n == 0) return DDMP_OK;
     DDMP_REQUIRE(rowptr && col && w && H && Y, "spmm_gcn: null pointer");
     cudaStream_t st = as_stream(stream);
     switch (C) {
-        case 32: return launch_spmm<32>(rowptr, col, w, H, bias, Y, stats_partials, n, st);
-        case 64: return launch_spmm<64>(rowptr, col, w, H, bias, Y, stats_partials, n, st);
-        case 128: return launch_spmm<128>(rowptr, col, w, H, bias, Y, stats_partials, n, st);
-        case 256: return launch_spmm<256>(rowptr, col, w, H, bias, Y, stats_partials, n, st);
-        case 512: return launch_spmm<512>(rowptr, col, w, H, bias, Y, stats_partials, n, st);
+        case 32: return launch_spmm<32>(rowptr, col, w, H, bias, Y, stats_partials, amax_blocks, n, st);
+        case 64: return launch_spmm<64>(rowptr, col, w, H, bias, Y, stats_partials, amax_blocks, n, st);
+        case 128: return launch_spmm<128>(rowptr, col, w, H, bias, Y, stats_partials, amax_blocks, n, st);
+        case 256: return launch_spmm<256>(rowptr, col, w, H, bias, Y, stats_partials, amax_blocks, n, st);
+        case 512: return launch_spmm<512>(rowptr, col, w, H, bias, Y, stats_partials, amax_blocks, n, st);
         default: break;
     }
-    if (stats_partials) {
-        set_error("spmm_gcn: BatchNorm statistics epilogue supports C in {32,64,128,256,512}, got %d", C);
+    if (stats_partials || amax_blocks) {
+        set_error("spmm_gcn: the statistics / amax epilogues support C in {32,64,128,256,512}, got %d", C);
         return DDMP_ERR_UNSUPPORTED;
     }
     spmm_gcn_generic_kernel<<<(unsigned)ceil_div(n, 8), 256, 0, st>>>(rowptr, col, w, H, bias, Y, n, C);

@@ -35,16 +35,23 @@ def num_row_blocks(n: int, C: int) -> int:
     return int(lib.query("ddmp_num_row_blocks", n, C))
 
 
-def spmm_gcn(graph: GcnGraph, H, bias=None, stats=False, transposed=False, out=None, n_rows=None):
-    """n_rows < H.shape[0] in the partitioned mode: H = [owned | halo] rows, only the owned rows are computed"""
+AMAX_WIDTHS = (64, 128, 256, 512)      # widths whose aggregation kernel has the amax epilogue and feed tensor-core GEMMs
+
+
+def spmm_gcn(graph: GcnGraph, H, bias=None, stats=False, transposed=False, out=None, n_rows=None, amax=False):
+    """n_rows < H.shape[0] in the partitioned mode: H = [owned | halo] rows, only the owned rows are computed.
+    ``amax``: also return the per-row-block maxima of |Y| (operand bound of the fp16-split GEMMs)"""
     n, C = H.shape
     if n_rows is not None:
         n = n_rows
     rowptr, col, w = (graph.rowptr_t, graph.col_t, graph.w_t) if transposed else (graph.rowptr, graph.col, graph.w)
     Y = out if out is not None else torch.empty(n, C, dtype=torch.float32, device=H.device)
     partials = torch.empty(num_row_blocks(n, C), 2, C, dtype=torch.float32, device=H.device) if stats else None
-    lib.call("ddmp_spmm_gcn", ptr(rowptr), ptr(col), ptr(w), ptr(H), ptr(bias), ptr(Y), ptr(partials), n, C,
+    ab = torch.empty(num_row_blocks(n, C), dtype=torch.float32, device=H.device) if amax else None
+    lib.call("ddmp_spmm_gcn", ptr(rowptr), ptr(col), ptr(w), ptr(H), ptr(bias), ptr(Y), ptr(partials), ptr(ab), n, C,
              stream_ptr(H.device))
+    if amax:
+        return (Y, partials, ab) if stats else (Y, ab)
     return (Y, partials) if stats else Y
 
 
@@ -57,35 +64,38 @@ def _gemm_ws(n, Cin, Cout, device, backend):
     return torch.empty(nbytes // 4, dtype=torch.float32, device=device), nbytes
 
 
-def gemm_xw(X, W, row_map=None, scale=None, shift=None, out=None, n=None, backend=None):
+def gemm_xw(X, W, row_map=None, scale=None, shift=None, out=None, n=None, backend=None, amax=None):
+    """``amax``: optional device tensor whose largest magnitude bounds |act(X)| -> fp16-split tensor-core kernel"""
     n = X.shape[0] if n is None else n
     Cout, Cin = W.shape
     H = out if out is not None else torch.empty(n, Cout, dtype=torch.float32, device=X.device)
     backend = GEMM_BACKEND if backend is None else backend
     ws, ws_bytes = _gemm_ws(n, Cin, Cout, X.device, backend)
     lib.call("ddmp_gemm_xw", ptr(X), ptr(row_map), ptr(scale), ptr(shift), SLOPE, ptr(W), ptr(H), ptr(ws), ws_bytes,
-             n, Cin, Cout, backend, stream_ptr(X.device))
+             n, Cin, Cout, ptr(amax), 0 if amax is None else amax.numel(), backend, stream_ptr(X.device))
     return H
 
 
-def gemm_dx(dH, W, out=None, backend=None):
+def gemm_dx(dH, W, out=None, backend=None, amax=None):
     n = dH.shape[0]
     Cout, Cin = W.shape
     gX = out if out is not None else torch.empty(n, Cin, dtype=torch.float32, device=dH.device)
     backend = GEMM_BACKEND if backend is None else backend
     ws, ws_bytes = _gemm_ws(n, Cin, Cout, dH.device, backend)
-    lib.call("ddmp_gemm_dx", ptr(dH), ptr(W), ptr(gX), ptr(ws), ws_bytes, n, Cin, Cout, backend,
-             stream_ptr(dH.device))
+    lib.call("ddmp_gemm_dx", ptr(dH), ptr(W), ptr(gX), ptr(ws), ws_bytes, n, Cin, Cout, ptr(amax),
+             0 if amax is None else amax.numel(), backend, stream_ptr(dH.device))
     return gX
 
 
-def gemm_dw(dH, X, Cin, row_map=None, scale=None, shift=None, backend=None):
+def gemm_dw(dH, X, Cin, row_map=None, scale=None, shift=None, backend=None, amax_dh=None, amax_x=None):
     n, Cout = dH.shape
     dW = torch.empty(Cout, Cin, dtype=torch.float32, device=dH.device)
     ws_bytes = int(lib.query("ddmp_gemm_dw_workspace_bytes", n, Cin, Cout))
     ws = torch.empty(max(ws_bytes, 16) // 4, dtype=torch.float32, device=dH.device)
     lib.call("ddmp_gemm_dw", ptr(dH), ptr(X), ptr(row_map), ptr(scale), ptr(shift), SLOPE, ptr(dW), ptr(ws),
-             ws_bytes, n, Cin, Cout, GEMM_BACKEND if backend is None else backend, stream_ptr(dH.device))
+             ws_bytes, n, Cin, Cout, ptr(amax_dh), 0 if amax_dh is None else amax_dh.numel(), ptr(amax_x),
+             0 if amax_x is None else amax_x.numel(), GEMM_BACKEND if backend is None else backend,
+             stream_ptr(dH.device))
     return dW
 
 
@@ -110,11 +120,16 @@ def colsum(X):
 
 def bn_stats_finalize(partials, n, gamma, beta, running_mean=None, running_var=None):
     nblk, _, C = partials.shape
-    stats = torch.empty(4, C, dtype=torch.float32, device=partials.device)   # mean, rstd, scale, shift
+    stats = torch.empty(5, C, dtype=torch.float32, device=partials.device)   # mean, rstd, scale, shift, bound
     lib.call("ddmp_bn_stats_finalize", ptr(partials), nblk, n, C, ptr(gamma), ptr(beta), BN_EPS, BN_MOMENTUM,
              ptr(running_mean), ptr(running_var), ptr(stats[0]), ptr(stats[1]), ptr(stats[2]), ptr(stats[3]),
-             stream_ptr(partials.device))
+             ptr(stats[4]), stream_ptr(partials.device))
     return stats
+
+
+def act_bound(stats):
+    """per-channel upper bound of |lrelu(scale*Y+shift)| (training-mode batch statistics only), else None"""
+    return stats[4] if stats.shape[0] > 4 else None
 
 
 def bn_lrelu_backward(gX, Y, stats, dY_out=None, comm=None):
@@ -229,7 +244,8 @@ class GcnNetFunction(torch.autograd.Function):
             if l == 0:
                 gemm_xw(x_in, Ws[0], row_map=graph.perm, out=H, n=n)
             else:
-                gemm_xw(Ys[l - 1], Ws[l], scale=stats[l - 1][2], shift=stats[l - 1][3], out=H)
+                gemm_xw(Ys[l - 1], Ws[l], scale=stats[l - 1][2], shift=stats[l - 1][3], out=H,
+                        amax=act_bound(stats[l - 1]))
             if comm is not None:
                 comm.exchange(H)
             if training:
@@ -300,6 +316,7 @@ class GcnNetFunction(torch.autograd.Function):
         for l in range(L - 1, -1, -1):
             cout, cin = Ws[l].shape
             dH = bufC[: n * cout].view(n, cout)
+            dh_max = None                           # row-block maxima of |dH| when the aggregation kernel provides them
             if comm is None and FUSE_BN_SPMM and graph.symmetric and cout in (32, 64, 128, 256, 512):
                 _, dgamma, dbeta, dbias = bn_bwd_spmm_fused(graph, gX, Ys[l], stats[l], dH_out=dH)
             else:
@@ -307,13 +324,17 @@ class GcnNetFunction(torch.autograd.Function):
                 _, dgamma, dbeta, dbias = bn_lrelu_backward(gX, Ys[l], stats[l], dY_out=dY, comm=comm)
                 if comm is not None:
                     comm.exchange(dY)               # A_hat symmetric: the backward needs dY of the halo rows
-                spmm_gcn(graph, dY, transposed=True, out=dH, n_rows=n)
+                if cout in AMAX_WIDTHS and l > 0:
+                    _, dh_max = spmm_gcn(graph, dY, transposed=True, out=dH, n_rows=n, amax=True)
+                else:
+                    spmm_gcn(graph, dY, transposed=True, out=dH, n_rows=n)
             if l == 0:
                 gW = gemm_dw(dH, x_in, cin, row_map=graph.perm)
             else:
-                gW = gemm_dw(dH, Ys[l - 1], cin, scale=stats[l - 1][2], shift=stats[l - 1][3])
+                gW = gemm_dw(dH, Ys[l - 1], cin, scale=stats[l - 1][2], shift=stats[l - 1][3], amax_dh=dh_max,
+                             amax_x=act_bound(stats[l - 1]) if dh_max is not None else None)
                 gX = bufA[: n * cin].view(n, cin)
-                gemm_dx(dH, Ws[l], out=gX)
+                gemm_dx(dH, Ws[l], out=gX, amax=dh_max)
             grads[4 * l: 4 * l + 4] = [gW, dbias, dgamma, dbeta]
         g_xpos = g_out if (kind == HEAD_POS and ctx.needs_input_grad[6]) else None
         ctx.Ys = ctx.stats = ctx.h_save = ctx.t_save = None

@@ -61,9 +61,11 @@ int ddmp_gcn_edge_weights(const int32_t* rowptr, const int32_t* col, float* w, i
 /* Y[i,:] = sum_k w[k] * H[col[k],:] (+ bias).  Optional epilogue statistics: stats_partials[b][0][c] = sum of
  * Y[:,c] over row block b, [b][1][c] = sum of Y^2 (BatchNorm partials).  The same call is the backward pass
  * (A_hat is symmetric): dH = spmm(dY) with bias = stats = NULL.  C must be a multiple of 4.
+ * amax_blocks (optional, [ddmp_num_row_blocks(n,C)]): max |Y| of every row block, the `amax` input of the dense
+ * transforms that consume Y.
  * [ref: GCNConv.propagate + bias at util/networks.py:51-62,112-123; torch_scatter.scatter_add] */
 int ddmp_spmm_gcn(const int32_t* rowptr, const int32_t* col, const float* w, const float* H, const float* bias,
-                  float* Y, float* stats_partials, int64_t n, int32_t C, void* stream);
+                  float* Y, float* stats_partials, float* amax_blocks, int64_t n, int32_t C, void* stream);
 
 /* Backward aggregation fused with ddmp_bn_bwd_apply:  dH = A_hat * dY  with dY recomputed on the fly from the gathered
  * rows of gX and Y (dY is never materialised); optional colsum_partials[b][0][c] = column sums of dY (conv bias
@@ -77,10 +79,12 @@ int ddmp_spmm_bn_bwd(const int32_t* rowptr, const int32_t* col, const float* w, 
 /* partials [nblk][2][C] -> batch mean / biased var; rstd = 1/sqrt(var+eps); scale = gamma*rstd;
  * shift = beta - mean*scale; running stats updated in place when non-NULL (momentum, unbiased var).
  * The normalise + LeakyReLU itself is applied lazily by the consumer (GEMM / head prologue).
+ * bound (optional, [C]): |gamma|*sqrt(n-1)+|beta| >= |scale*y+shift| for every row of the batch (the `amax` input
+ * of the dense transforms).
  * [ref: nn.BatchNorm1d at util/networks.py:31-42,51-62] */
 int ddmp_bn_stats_finalize(const float* partials, int64_t nblk, int64_t n, int32_t C, const float* gamma,
                            const float* beta, float eps, float momentum, float* running_mean, float* running_var,
-                           float* mean, float* rstd, float* scale, float* shift, void* stream);
+                           float* mean, float* rstd, float* scale, float* shift, float* bound, void* stream);
 /* Backward of LeakyReLU(BN(Y)) given gX = dL/d(activated output):  gZ = gX * lrelu'(scale*Y+shift),
  * xhat = (Y-mean)*rstd;  partials[b][0][c] = sum gZ, [b][1][c] = sum gZ*xhat. */
 int ddmp_bn_bwd_reduce(const float* gX, const float* Y, const float* mean, const float* rstd, const float* scale,
@@ -108,18 +112,24 @@ int ddmp_gather_rows(const float* src, const int32_t* idx, float* dst, int64_t m
  * [ref: GCNConv.lin at util/networks.py:51-62 — cuBLAS SGEMM] */
 int ddmp_gemm_xw(const float* X, const int32_t* row_map, const float* scale, const float* shift, float slope,
                  const float* W, float* H, void* workspace, int64_t workspace_bytes, int64_t n, int32_t Cin,
-                 int32_t Cout, int backend, void* stream);
+                 int32_t Cout, const float* amax, int64_t amax_len, int backend, void* stream);
+/* `amax` (optional, device, amax_len floats): max |amax[i]| is an upper bound of the magnitude of the left operand
+ * (act(X) resp. dH).  With a bound the tensor-core path multiplies with three fp16 MMAs per product (operands
+ * scaled by powers of two into the fp16 range, fp32 accumulation, accuracy of an fp32 product sum) at twice the
+ * rate of the bound-free 3xTF32 kernels; results are wrong only if the bound is violated by more than 2x. */
 /* scratch the tensor-core path of gemm_xw / gemm_dx needs for the pre-split, pre-swizzled weight image (0 when the
  * shape runs on the FFMA kernel; with workspace == NULL the FFMA kernel is used). */
 int64_t ddmp_gemm_workspace_bytes(int64_t n, int32_t Cin, int32_t Cout);
 /* gX[n,Cin] = dH[n,Cout] * W[Cout,Cin]. */
 int ddmp_gemm_dx(const float* dH, const float* W, float* gX, void* workspace, int64_t workspace_bytes, int64_t n,
-                 int32_t Cin, int32_t Cout, int backend, void* stream);
-/* dW[Cout,Cin] = dH[n,Cout]^T * act(X)[n,Cin]; deterministic split-K over rows through `workspace`. */
+                 int32_t Cin, int32_t Cout, const float* amax, int64_t amax_len, int backend, void* stream);
+/* dW[Cout,Cin] = dH[n,Cout]^T * act(X)[n,Cin]; deterministic split-K over rows through `workspace`.
+ * amax_dh / amax_x (optional, both or neither): bounds of |dH| and |act(X)| as for ddmp_gemm_xw. */
 int64_t ddmp_gemm_dw_workspace_bytes(int64_t n, int32_t Cin, int32_t Cout);
 int ddmp_gemm_dw(const float* dH, const float* X, const int32_t* row_map, const float* scale, const float* shift,
                  float slope, float* dW, void* workspace, int64_t workspace_bytes, int64_t n, int32_t Cin,
-                 int32_t Cout, int backend, void* stream);
+                 int32_t Cout, const float* amax_dh, int64_t amax_dh_len, const float* amax_x, int64_t amax_x_len,
+                 int backend, void* stream);
 
 /* ---- network heads (32 -> 16 -> 3) ------------------------------------------------------------------------ */
 /* x = lrelu(scale*Y12+shift); h = lrelu(W1 x + b1); o = W2 h + b2;

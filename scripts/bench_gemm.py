@@ -12,9 +12,13 @@ for cin, cout in shapes:
     X = torch.randn(n, cin, device=dev); W = torch.randn(cout, cin, device=dev) / cin ** 0.5
     dH = torch.randn(n, cout, device=dev)
     sc = torch.rand(cin, device=dev) + 0.5; sh = torch.randn(cin, device=dev)
-    for name, fn in (("xw", lambda b: F_.gemm_xw(X, W, scale=sc, shift=sh, backend=b)),
-                     ("dx", lambda b: F_.gemm_dx(dH, W, backend=b)),
-                     ("dw", lambda b: F_.gemm_dw(dH, X, cin, scale=sc, shift=sh, backend=b))):
+    bx = (torch.nn.functional.leaky_relu(X[:65536] * sc + sh, 0.01).abs().amax(0) * 1.5).contiguous()
+    bd = dH[:65536].abs().amax(0).mul(1.5).contiguous()
+    F16 = os.environ.get("BENCH_F16", "1") == "1"
+    for name, fn in (("xw", lambda b: F_.gemm_xw(X, W, scale=sc, shift=sh, backend=b, amax=bx if (F16 and b == 2) else None)),
+                     ("dx", lambda b: F_.gemm_dx(dH, W, backend=b, amax=bd if (F16 and b == 2) else None)),
+                     ("dw", lambda b: F_.gemm_dw(dH, X, cin, scale=sc, shift=sh, backend=b, amax_dh=bd if (F16 and b == 2) else None,
+                                                 amax_x=bx if (F16 and b == 2) else None))):
         for b in (1, 2):
             try:
                 fn(b); torch.cuda.synchronize()

@@ -301,6 +301,55 @@ def test_gemm_tcgen05_3xtf32(cin, cout, n):
     assert rel_err(a, F_.gemm_xw(Xn, Wd, scale=sc, shift=sh, backend=1)) < 1e-5
 
 
+@pytest.mark.parametrize("cin,cout", TC_SHAPES)
+@pytest.mark.parametrize("n", [640, 4099, 20011])
+def test_gemm_tcgen05_f16_split(cin, cout, n):
+    """tcgen05 kind::f16 path (x*s = hi + lo in fp16, three MMAs, fp32 accumulate) given an operand bound: accuracy of
+    an fp32 product sum against a float64 evaluation, for O(1) activations, for tiny gradients, and with a bound that
+    is 1000x pessimistic (the BatchNorm bound at 1M rows)"""
+    from dual_dmp_b200 import functional as F_
+    torch.manual_seed(cin * 1000 + cout + n)
+    X = torch.randn(n + 5, cin) * (torch.rand(1, cin) * 3 + 0.1)
+    W = torch.randn(cout, cin) / cin ** 0.5
+    W[3] = 0.0                                        # an all-zero weight row
+    W[5] *= 1e-6
+    scale, shift = torch.rand(cin) + 0.5, torch.randn(cin)
+    rmap = torch.randperm(n + 5)[:n].to(torch.int32)
+    dH = torch.randn(n, cout) * 1e-7 * torch.exp(torch.randn(n, 1))
+    Xd, Wd, dHd = X.to(DEV), W.to(DEV), dH.to(DEV)
+    sc, sh, rm = scale.to(DEV), shift.to(DEV), rmap.to(DEV)
+    Xn = Xd[:n].contiguous()
+    act = torch.nn.functional.leaky_relu(X.double() * scale.double() + shift.double(), 0.01)
+    b_raw = X.abs().amax(0).to(DEV)                   # per-channel bounds (any array whose max bounds the operand)
+    b_act = act.abs().amax(0).float().to(DEV)
+    b_dh = dH.abs().amax(1)[::7].contiguous().to(DEV) if n > 700 else dH.abs().amax().reshape(1).to(DEV)
+    b_dh = torch.cat([b_dh, dH.abs().amax().reshape(1).to(DEV)])
+    e1 = rel_err(F_.gemm_xw(Xn, Wd, backend=2, amax=b_raw), X[:n].double() @ W.double().t())
+    e2 = rel_err(F_.gemm_xw(Xn, Wd, scale=sc, shift=sh, backend=2, amax=b_act), act[:n] @ W.double().t())
+    e2p = rel_err(F_.gemm_xw(Xn, Wd, scale=sc, shift=sh, backend=2, amax=b_act * 1000.0), act[:n] @ W.double().t())
+    e3 = rel_err(F_.gemm_xw(Xd, Wd, row_map=rm, n=n, backend=2, amax=b_raw), X[rmap.long()].double() @ W.double().t())
+    e4 = rel_err(F_.gemm_dx(dHd, Wd, backend=2, amax=b_dh), dH.double() @ W.double())
+    t2 = rel_err(F_.gemm_xw(Xn, Wd, scale=sc, shift=sh, backend=2), act[:n] @ W.double().t())     # 3xTF32, same job
+    t4 = rel_err(F_.gemm_dx(dHd, Wd, backend=2), dH.double() @ W.double())
+    e5 = rel_err(F_.gemm_dw(dHd, Xn, cin, backend=2, amax_dh=b_dh, amax_x=b_raw), dH.double().t() @ X[:n].double())
+    e6 = rel_err(F_.gemm_dw(dHd, Xn, cin, scale=sc, shift=sh, backend=2, amax_dh=b_dh, amax_x=b_act * 1000.0),
+                 dH.double().t() @ act[:n])
+    t6 = rel_err(F_.gemm_dw(dHd, Xn, cin, scale=sc, shift=sh, backend=2), dH.double().t() @ act[:n])
+    assert max(e5, e6) < 2e-5 and e6 < 1.5 * t6 + 1e-7, (e5, e6, t6)
+    assert torch.equal(F_.gemm_dw(dHd, Xn, cin, scale=sc, shift=sh, backend=2, amax_dh=b_dh, amax_x=b_act),
+                       F_.gemm_dw(dHd, Xn, cin, scale=sc, shift=sh, backend=2, amax_dh=b_dh, amax_x=b_act))
+    report(f"gemm_tc f16 cin={cin} cout={cout} n={n}", (e1, e2, e2p, e3, e4, e5, e6, "tf32:", t2, t4, t6))
+    # the error is dominated by the tensor core's truncating fp32 accumulation (grows with K, same for 3xTF32)
+    assert max(e1, e2, e2p, e3, e4) < 5e-6, (e1, e2, e2p, e3, e4)
+    assert e2 < 1.5 * t2 + 1e-7 and e4 < 1.5 * t4 + 1e-7, (e2, t2, e4, t4)
+    a = F_.gemm_xw(Xn, Wd, scale=sc, shift=sh, backend=2, amax=b_act)
+    assert torch.equal(a, F_.gemm_xw(Xn, Wd, scale=sc, shift=sh, backend=2, amax=b_act))
+    assert (a[:, 3] == 0).all()
+    ref5 = act[:n] @ W[5].double()
+    assert rel_err(a[:, 5], ref5) < 5e-6              # a weight row 1e-6 of the others keeps full accuracy
+    assert rel_err(a, F_.gemm_xw(Xn, Wd, scale=sc, shift=sh, backend=2)) < 5e-6       # vs the 3xTF32 kernel
+
+
 def test_fused_clip_adam_matches_torch():
     """ddmp_grad_norm + ddmp_adam_step_dev over flat buffers == clip_grad_norm_ + torch.optim.Adam (main.py:108-110)"""
     from dual_dmp_b200.step import FusedAdam
