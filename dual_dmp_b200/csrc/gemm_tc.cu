@@ -1062,6 +1062,7 @@ struct Nt16Args {
     float slope;
     const float* amax;       // bound of |act(A)|: max over this array
     int64_t amax_len;
+    unsigned long long* trace;   // profiling only (DDMP_TC_TRACE=1): per-role cycle counters of CTA 0
     int flags;               // bit 0: prefetch the next tile's A rows into L2
     int64_t M;
     int N, K;
@@ -1069,23 +1070,57 @@ struct Nt16Args {
     int64_t num_tiles;
 };
 
-// A-operand producer of the fp16-split NT kernels: thread (row group t>>3, chunk c = t&7) handles 8 consecutive k of
-// NJ rows.  Loads first (so the wait for a free stage overlaps them), then transform + split + swizzled stores.
-template <int NJ, class Args>
-__device__ __forceinline__ void produce_load(const Args& g, const int64_t (&src_row)[NJ], int k0, float4 (&av)[NJ][2]) {
+// A-operand producer of the fp16-split NT kernels.  16 consecutive lanes read the 256 bytes (64 fp32) a row
+// contributes to the k-block, so one warp-wide 16-byte load covers 2 rows x 256 B = four full 128-byte lines (an
+// earlier mapping gave every thread 8 consecutive k as two 16-byte loads: each warp load then touched eight
+// half-used lines and the LSU data pipe, at 77 % busy, bounded the kernel: ncu, profiles/).  A thread's 4 k values
+// become 8 bytes of hi and 8 bytes of lo; the pair of lanes that shares a 16-byte swizzle chunk writes its halves.
+// Loads first (so the wait for a free stage overlaps them), then transform + split + swizzled stores.
+constexpr int kProdNJ = BM * 16 / kProducerThreads;      // rows per thread per k-block (8)
+constexpr int kProdRPP = kProducerThreads / 16;          // rows covered by one pass of the producer threads (16)
+__device__ __forceinline__ void sts64(uint32_t saddr, uint32_t x, uint32_t y) {
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(saddr), "r"(x), "r"(y) : "memory");
+}
+template <class Args>
+__device__ __forceinline__ void produce_load(const Args& g, const int64_t (&src_row)[kProdNJ], int k0,
+                                             float4 (&av)[kProdNJ]) {
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) {
-        if (src_row[j] >= 0) {
-            av[j][0] = ldg4(g.A + src_row[j] * g.K + k0);
-            av[j][1] = ldg4(g.A + src_row[j] * g.K + k0 + 4);
+    for (int j = 0; j < kProdNJ; ++j)
+        av[j] = (src_row[j] >= 0) ? ldg4(g.A + src_row[j] * g.K + k0) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+template <class Args>
+__device__ __forceinline__ void produce_store(const Args& g, const int64_t (&src_row)[kProdNJ], int k0,
+                                              float4 (&av)[kProdNJ], float s_a, bool has_act, int t, uint32_t st,
+                                              uint32_t a_bytes) {
+    // the power-of-two operand scale is folded into the affine part (LeakyReLU is positively homogeneous)
+    float4 sc = make_float4(s_a, s_a, s_a, s_a), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (has_act) {
+        sc = ldg4(g.scale + k0);
+        sh = ldg4(g.shift + k0);
+        sc.x *= s_a; sc.y *= s_a; sc.z *= s_a; sc.w *= s_a;
+        sh.x *= s_a; sh.y *= s_a; sh.z *= s_a; sh.w *= s_a;
+    }
+    const uint32_t c4 = t & 15;                           // float4 index inside the row's 256 bytes
+#pragma unroll
+    for (int j = 0; j < kProdNJ; ++j) {
+        const uint32_t row = (t >> 4) + j * kProdRPP;
+        float4 a = av[j];
+        if (has_act) {
+            if (src_row[j] >= 0) {
+                a.x = lrelu_max(fmaf(a.x, sc.x, sh.x), g.slope); a.y = lrelu_max(fmaf(a.y, sc.y, sh.y), g.slope);
+                a.z = lrelu_max(fmaf(a.z, sc.z, sh.z), g.slope); a.w = lrelu_max(fmaf(a.w, sc.w, sh.w), g.slope);
+            }
         } else {
-            av[j][0] = av[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            a.x *= s_a; a.y *= s_a; a.z *= s_a; a.w *= s_a;
         }
+        uint32_t h0, l0, h1, l1;
+        split_f16x2(a.x, a.y, h0, l0);
+        split_f16x2(a.z, a.w, h1, l1);
+        const uint32_t off = sw128(row, c4 >> 1) + ((c4 & 1u) << 3);
+        sts64(st + off, h0, h1);
+        sts64(st + a_bytes + off, l0, l1);
     }
 }
-template <int NJ, int RPP, class Args>
-__device__ __forceinline__ void produce_store(const Args& g, const int64_t (&src_row)[NJ], int k0, float4 (&av)[NJ][2],
-                                              float s_a, bool has_act, int t, uint32_t st, uint32_t a_bytes);
 // A k-block touches 256 bytes of each of the tile's 128 rows (stride K*4), and the next 256 bytes of the same rows a
 // microsecond later: DRAM sees short scattered bursts (measured: every shape of the fp16-split kernel ran at
 // ~3.6 TB/s of operand + result traffic).  Pulling the NEXT tile's rows into L2 as whole rows while the current tile
@@ -1099,102 +1134,202 @@ __device__ __forceinline__ void prefetch_tile_l2(const Args& g, int64_t m0) {
     const int64_t r = g.a_map ? (int64_t)__ldg(g.a_map + m) : m;
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(g.A + r * g.K), "r"((uint32_t)g.K * 4u) : "memory");
 }
-// The producer loop of a CTA.  (Issuing the loads one k-block further ahead from a second register buffer was
-// measured slower for both splits; so were L1::no_allocate loads: a thread's two 16-byte loads share a sector.)
+// 16-byte read-only load the compiler may not move: the prefetch below depends on the loads of the NEXT k-block being
+// issued before the current one is transformed (plain __ldg loads get sunk below the transform to save registers).
+__device__ __forceinline__ float4 ldg4_pinned(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+// The producer loop of a CTA: (tile, k-block) pairs flattened, the loads of pair i+1 in flight while pair i is
+// transformed (two register buffers, ping-pong by unrolling).  Cycle counters (DDMP_TC_TRACE) showed the producers,
+// not the tensor pipe, set the pace of the fp16-split kernel: per k-block 420 cycles issuing loads, ~100 waiting for
+// a free stage and 1600 between the wait and the arrive, most of it load latency, while the MMA thread waited
+// 1100 cycles per k-block for `full`.
 template <int STAGES, class Args, class WaitEmpty>
 __device__ __forceinline__ void produce_loop_simple(const Args& g, int64_t first_tile, int64_t tile_step, int64_t row_mul,
                                                     int64_t row_add, int num_kb, float s_a, uint32_t smem_base,
                                                     uint32_t stage_bytes, uint32_t a_bytes, uint64_t* full_bar,
                                                     uint64_t* empty_bar, WaitEmpty wait_empty) {
-    constexpr int NJ = BM * 8 / kProducerThreads;
-    constexpr int RPP = kProducerThreads / 8;
+    constexpr int NJ = kProdNJ, RPP = kProdRPP;
     const int t = threadIdx.x, lane = threadIdx.x & 31;
-    const int c8 = (t & 7) * 8;
+    const int c8 = (t & 15) * 4;
+    const uint32_t c4 = t & 15;
     const bool has_act = g.scale != nullptr;
-    uint32_t it = 0;
-    for (int64_t tile = first_tile; tile < g.num_tiles; tile += tile_step) {
+    const int64_t my_tiles = first_tile < g.num_tiles ? (g.num_tiles - first_tile + tile_step - 1) / tile_step : 0;
+    const uint32_t total = (uint32_t)(my_tiles * num_kb);
+    // load cursor
+    int64_t lc_tile = first_tile;
+    int lc_kb = 0;
+    const float* rp[NJ];                                  // row pointers of the cursor's tile (nullptr: past the end)
+    auto set_rows = [&](int64_t tile) {
         const int64_t m0 = (tile / g.tiles_n) * row_mul + row_add;
-        if ((g.flags & 1) && tile + tile_step < g.num_tiles)
-            prefetch_tile_l2(g, ((tile + tile_step) / g.tiles_n) * row_mul + row_add);
-        int64_t src_row[NJ];
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
-            const int64_t m = m0 + (t >> 3) + j * RPP;
-            src_row[j] = (m < g.M) ? (g.a_map ? (int64_t)__ldg(g.a_map + m) : m) : -1;
+            const int64_t m = m0 + (t >> 4) + j * RPP;
+            const int64_t r = (m < g.M) ? (g.a_map ? (int64_t)__ldg(g.a_map + m) : m) : -1;
+            rp[j] = r >= 0 ? g.A + r * g.K + c8 : nullptr;
         }
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-            const int s = it % STAGES;
-            const uint32_t ph = (it / STAGES) & 1;
-            float4 av[NJ][2];
-            produce_load<NJ>(g, src_row, kb * BK16 + c8, av);
-            wait_empty(empty_bar + s, ph ^ 1u);
-            produce_store<NJ, RPP>(g, src_row, kb * BK16 + c8, av, s_a, has_act, t, smem_base + s * stage_bytes, a_bytes);
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(full_bar + s);
-        }
-    }
-}
-template <int NJ, int RPP, class Args>
-__device__ __forceinline__ void produce_store(const Args& g, const int64_t (&src_row)[NJ], int k0, float4 (&av)[NJ][2],
-                                              float s_a, bool has_act, int t, uint32_t st, uint32_t a_bytes) {
-    // the power-of-two operand scale is folded into the affine part (LeakyReLU is positively homogeneous)
-    float4 sc0 = make_float4(s_a, s_a, s_a, s_a), sc1 = sc0;
-    float4 sh0 = make_float4(0.f, 0.f, 0.f, 0.f), sh1 = sh0;
-    if (has_act) {
-        sc0 = ldg4(g.scale + k0); sc1 = ldg4(g.scale + k0 + 4);
-        sh0 = ldg4(g.shift + k0); sh1 = ldg4(g.shift + k0 + 4);
-        sc0.x *= s_a; sc0.y *= s_a; sc0.z *= s_a; sc0.w *= s_a; sc1.x *= s_a; sc1.y *= s_a; sc1.z *= s_a; sc1.w *= s_a;
-        sh0.x *= s_a; sh0.y *= s_a; sh0.z *= s_a; sh0.w *= s_a; sh1.x *= s_a; sh1.y *= s_a; sh1.z *= s_a; sh1.w *= s_a;
-    }
-    const uint32_t c = t & 7;
+        if ((g.flags & 1) && tile + tile_step < g.num_tiles)
+            prefetch_tile_l2(g, ((tile + tile_step) / g.tiles_n) * row_mul + row_add);
+    };
+    auto load = [&](float4 (&buf)[NJ], uint32_t& vmask, int& k0) {
+        k0 = lc_kb * BK16;
+        vmask = 0;
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) {
-        const uint32_t row = (t >> 3) + j * RPP;
-        float4 a = av[j][0], b = av[j][1];
-        if (has_act) {
-            if (src_row[j] >= 0) {
-                a.x = lrelu_max(fmaf(a.x, sc0.x, sh0.x), g.slope); a.y = lrelu_max(fmaf(a.y, sc0.y, sh0.y), g.slope);
-                a.z = lrelu_max(fmaf(a.z, sc0.z, sh0.z), g.slope); a.w = lrelu_max(fmaf(a.w, sc0.w, sh0.w), g.slope);
-                b.x = lrelu_max(fmaf(b.x, sc1.x, sh1.x), g.slope); b.y = lrelu_max(fmaf(b.y, sc1.y, sh1.y), g.slope);
-                b.z = lrelu_max(fmaf(b.z, sc1.z, sh1.z), g.slope); b.w = lrelu_max(fmaf(b.w, sc1.w, sh1.w), g.slope);
+        for (int j = 0; j < NJ; ++j) {
+            if (rp[j]) {
+                buf[j] = ldg4_pinned(rp[j] + k0);
+                vmask |= 1u << j;
+            } else {
+                buf[j] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
-        } else {
-            a.x *= s_a; a.y *= s_a; a.z *= s_a; a.w *= s_a; b.x *= s_a; b.y *= s_a; b.z *= s_a; b.w *= s_a;
         }
-        uint4 hi, lo;
-        split_f16x8(a, b, hi, lo);
-        const uint32_t off = sw128(row, c);
-        sts128(st + off, hi);
-        sts128(st + a_bytes + off, lo);
+        if (++lc_kb == num_kb) {
+            lc_kb = 0;
+            lc_tile += tile_step;
+            if (lc_tile < g.num_tiles) set_rows(lc_tile);
+        }
+    };
+    auto process = [&](float4 (&buf)[NJ], uint32_t vmask, int k0, uint32_t it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        const bool tr = g.trace && blockIdx.x == 0 && t == 0;
+        long long c1 = 0, c2 = 0, c3 = 0;
+        // the power-of-two operand scale is folded into the affine part (LeakyReLU is positively homogeneous)
+        float4 sc = make_float4(s_a, s_a, s_a, s_a), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (has_act) {
+            sc = ldg4(g.scale + k0 + c8);
+            sh = ldg4(g.shift + k0 + c8);
+            sc.x *= s_a; sc.y *= s_a; sc.z *= s_a; sc.w *= s_a;
+            sh.x *= s_a; sh.y *= s_a; sh.z *= s_a; sh.w *= s_a;
+        }
+        if (tr) c1 = clock64();
+        wait_empty(empty_bar + s, ph ^ 1u);
+        if (tr) c2 = clock64();
+        const uint32_t st = smem_base + s * stage_bytes;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            const uint32_t row = (t >> 4) + j * RPP;
+            float4 a = buf[j];
+            if (has_act) {
+                if (vmask & (1u << j)) {
+                    a.x = lrelu_max(fmaf(a.x, sc.x, sh.x), g.slope); a.y = lrelu_max(fmaf(a.y, sc.y, sh.y), g.slope);
+                    a.z = lrelu_max(fmaf(a.z, sc.z, sh.z), g.slope); a.w = lrelu_max(fmaf(a.w, sc.w, sh.w), g.slope);
+                }
+            } else {
+                a.x *= s_a; a.y *= s_a; a.z *= s_a; a.w *= s_a;
+            }
+            uint32_t h0, l0, h1, l1;
+            split_f16x2(a.x, a.y, h0, l0);
+            split_f16x2(a.z, a.w, h1, l1);
+            const uint32_t off = sw128(row, c4 >> 1) + ((c4 & 1u) << 3);
+            sts64(st + off, h0, h1);
+            sts64(st + a_bytes + off, l0, l1);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (tr) c3 = clock64();
+        if (lane == 0) mbar_arrive(full_bar + s);
+        if (tr) {
+            g.trace[1] += (unsigned long long)(c2 - c1);     // wait for a free stage
+            g.trace[2] += (unsigned long long)(c3 - c2);     // wait for data + transform + stores + fence
+            g.trace[3] += 1ull;
+        }
+    };
+    float4 buf0[NJ], buf1[NJ];
+    uint32_t vm0 = 0, vm1 = 0;
+    int k0 = 0, k1 = 0;
+    if (total > 0) {
+        set_rows(lc_tile);
+        load(buf0, vm0, k0);
+    }
+    for (uint32_t it = 0; it < total; it += 2) {
+        if (it + 1 < total) load(buf1, vm1, k1);
+        process(buf0, vm0, k0, it);
+        if (it + 1 >= total) break;
+        if (it + 2 < total) load(buf0, vm0, k0);
+        process(buf1, vm1, k1, it + 1);
     }
 }
-// epilogue of the fp16-split NT kernels: 32 columns of this thread's row, unscaled, through the swizzled staging tile
+// Epilogue of the fp16-split NT kernels: one warp drains its 32 rows x BN columns of the accumulator.
+// tcgen05.ld hands every thread one ROW; the 32 x 32 block goes through a swizzled staging tile so that a store
+// instruction writes 4 rows x 128 B, and the column scales are applied on the way out (there a lane owns 4 fixed
+// columns, so one 16-byte load of the scales serves the whole block).  The TMEM load of the next block is in flight
+// while the current one is written: the drain of a 128 x 256 tile took 13.5 k cycles when everything was serial,
+// which is what bounded the K <= 256 shapes (4 k-blocks of ~2.9 k cycles per tile).
+__device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 template <class Args>
-__device__ __forceinline__ void epilogue_store32(const Args& g, uint32_t (&v)[32], float inv_sa, uint32_t stg, int lane,
+__device__ __forceinline__ void epilogue_block32(const Args& g, uint32_t (&v)[32], float inv_sa, uint32_t stg, int lane,
                                                  int64_t mrow0, int ncol0) {
+    const int cc = lane & 7;
+    const bool tr = g.trace && blockIdx.x == 0 && threadIdx.x == 12 * 32;
+    long long p0 = 0, p1 = 0, p2 = 0;
+    if (tr) p0 = clock64();
+    float4 w = ldg4(g.inv_sw + ncol0 + cc * 4);          // scales of the 4 columns this lane stores
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {            // row = lane, 16-byte chunk i -> swizzled chunk i ^ (lane & 7)
-        const float4 w = ldg4(g.inv_sw + ncol0 + 4 * i);
-        uint4 o;
-        o.x = __float_as_uint(__uint_as_float(v[4 * i]) * inv_sa * w.x);
-        o.y = __float_as_uint(__uint_as_float(v[4 * i + 1]) * inv_sa * w.y);
-        o.z = __float_as_uint(__uint_as_float(v[4 * i + 2]) * inv_sa * w.z);
-        o.w = __float_as_uint(__uint_as_float(v[4 * i + 3]) * inv_sa * w.w);
-        sts128(stg + (uint32_t)lane * 128u + (uint32_t)((i ^ (lane & 7)) << 4), o);
-    }
+    for (int i = 0; i < 8; ++i)              // row = lane, 16-byte chunk i -> swizzled chunk i ^ (lane & 7)
+        sts128(stg + (uint32_t)lane * 128u + (uint32_t)((i ^ (lane & 7)) << 4),
+               make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+    w.x *= inv_sa; w.y *= inv_sa; w.z *= inv_sa; w.w *= inv_sa;
     __syncwarp();
+    if (tr) p1 = clock64();
+    uint4 o[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const int r = j * 4 + (lane >> 3), cc = lane & 7;
-        uint4 o;
+        const int r = j * 4 + (lane >> 3);
         asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                     : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w)
+                     : "=r"(o[j].x), "=r"(o[j].y), "=r"(o[j].z), "=r"(o[j].w)
                      : "r"(stg + (uint32_t)r * 128u + (uint32_t)((cc ^ (r & 7)) << 4)));
-        const int64_t m = mrow0 + r;
-        if (m < g.M) *reinterpret_cast<uint4*>(g.C + m * g.N + ncol0 + cc * 4) = o;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int64_t m = mrow0 + j * 4 + (lane >> 3);
+        if (m < g.M)
+            st4(g.C + m * g.N + ncol0 + cc * 4,
+                make_float4(__uint_as_float(o[j].x) * w.x, __uint_as_float(o[j].y) * w.y, __uint_as_float(o[j].z) * w.z,
+                            __uint_as_float(o[j].w) * w.w));
     }
     __syncwarp();
+    if (tr) {
+        p2 = clock64();
+        g.trace[11] += (unsigned long long)(p1 - p0);    // registers -> staging
+        g.trace[12] += (unsigned long long)(p2 - p1);    // staging -> global
+    }
+}
+// taddr = TMEM address of (this warp's lane quarter, first column of the accumulator buffer)
+template <int BN, class Args>
+__device__ __forceinline__ void epilogue_tile(const Args& g, uint32_t taddr, float inv_sa, uint32_t stg, int lane,
+                                              int64_t mrow0, int n0) {
+    static_assert(BN % 64 == 0, "two 32-column blocks per iteration");
+    uint32_t va[32], vb[32];
+    tmem_ld32_async(taddr, va);
+#pragma unroll 1
+    for (int cb = 0; cb < BN; cb += 64) {
+        const bool tr = g.trace && blockIdx.x == 0 && threadIdx.x == 12 * 32;
+        long long q0 = 0;
+        if (tr) q0 = clock64();
+        tmem_wait_ld();                                  // va has landed
+        if (tr) g.trace[13] += (unsigned long long)(clock64() - q0);   // exposed TMEM load latency
+        tmem_ld32_async(taddr + (uint32_t)cb + 32u, vb);
+        epilogue_block32(g, va, inv_sa, stg, lane, mrow0, n0 + cb);
+        tmem_wait_ld();                                  // vb has landed
+        if (cb + 64 < BN) tmem_ld32_async(taddr + (uint32_t)cb + 64u, va);
+        epilogue_block32(g, vb, inv_sa, stg, lane, mrow0, n0 + cb + 32);
+    }
 }
 
 // W [N,K] (or, transposed, W^T given as [K,N]) -> per-row scaled fp16 hi/lo image; one warp per weight row n
@@ -1353,12 +1488,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) tc_gemm_nt16_kernel(const Nt16A
             const int n0 = (int)(tile % g.tiles_n) * BN;
             mbar_wait(acc_full + buf, (tile_no >> 1) & 1u);
             tc_fence_after();
-#pragma unroll 1
-            for (int cb = 0; cb < BN; cb += 32) {
-                uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)cb, v);
-                epilogue_store32(g, v, inv_sa, stg, lane, mrow0, n0 + cb);
-            }
+            epilogue_tile<BN>(g, tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN, inv_sa, stg, lane, mrow0, n0);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty + buf);
@@ -1462,14 +1592,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kV2Threads, 1) tc_ge
                 constexpr uint32_t idesc = make_idesc16(2 * BM, BN, false, false);
                 for (int64_t tile = pair; tile < g.num_tiles; tile += num_pairs, ++tile_no) {
                     const uint32_t buf = tile_no & 1u;
+                    long long a0 = 0;
+                    if (g.trace && blockIdx.x == 0) a0 = clock64();
                     mbar_wait_cluster(acc_empty + buf, ((tile_no >> 1) & 1u) ^ 1u);
+                    if (g.trace && blockIdx.x == 0) g.trace[7] += (unsigned long long)(clock64() - a0);   // wait acc free
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + buf * BN;
                     for (int kb = 0; kb < num_kb; ++kb, ++it) {
                         const int s = it % STAGES;
                         const uint32_t ph = (it / STAGES) & 1;
+                        const bool tr = g.trace && blockIdx.x == 0;
+                        long long c0 = 0, c1 = 0, c2 = 0;
+                        if (tr) c0 = clock64();
                         mbar_wait(full_bar + s, ph);
+                        if (tr) c1 = clock64();
                         mbar_wait_cluster(peer_ready + s, ph);
+                        if (tr) {
+                            c2 = clock64();
+                            g.trace[4] += (unsigned long long)(c1 - c0);     // MMA thread: wait own stage full
+                            g.trace[5] += (unsigned long long)(c2 - c1);     // wait peer stage full
+                            g.trace[6] += 1ull;
+                        }
                         tc_fence_after();
                         const uint32_t sa = smem_base + s * STAGE_BYTES;
 #pragma unroll
@@ -1526,16 +1669,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kV2Threads, 1) tc_ge
             const uint32_t buf = tile_no & 1u;
             const int64_t mrow0 = (tile / g.tiles_n) * (2 * BM) + rank * BM + q * 32;
             const int n0 = (int)(tile % g.tiles_n) * BN;
+            const bool tr = g.trace && blockIdx.x == 0 && warp == 12 && lane == 0;
+            long long e0 = 0, e1 = 0;
+            if (tr) e0 = clock64();
             mbar_wait_cluster(acc_full + buf, (tile_no >> 1) & 1u);
+            if (tr) e1 = clock64();
             tc_fence_after();
-#pragma unroll 1
-            for (int cb = 0; cb < BN; cb += 32) {
-                uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)cb, v);
-                epilogue_store32(g, v, inv_sa, stg, lane, mrow0, n0 + cb);
-            }
+            epilogue_tile<BN>(g, tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN, inv_sa, stg, lane, mrow0, n0);
             tc_fence_before();
             __syncwarp();
+            if (tr) {
+                g.trace[8] += (unsigned long long)(e1 - e0);                 // epilogue: wait accumulator
+                g.trace[9] += (unsigned long long)(clock64() - e1);          // epilogue: drain
+                g.trace[10] += 1ull;
+            }
             if (lane == 0) {
                 if (rank == 0) mbar_arrive(acc_empty + buf);
                 else mbar_arrive_remote(acc_empty + buf, 0);
@@ -1583,11 +1730,33 @@ static int run_nt16(const float* A, const int* a_map, const float* scale, const 
     g.slope = slope; g.amax = amax; g.amax_len = amax_len;
     static const int flags = [] { const char* e = getenv("DDMP_TC_F16_FLAGS"); return e ? atoi(e) : 0; }();
     g.flags = flags;
+    static const bool trace = [] { const char* e = getenv("DDMP_TC_TRACE"); return e && e[0] == '1'; }();
+    static unsigned long long* trace_buf = nullptr;
+    if (trace) {
+        if (!trace_buf) cudaMalloc(&trace_buf, 16 * sizeof(unsigned long long));
+        cudaMemsetAsync(trace_buf, 0, 16 * sizeof(unsigned long long), st);
+        g.trace = trace_buf;
+    }
+    auto dump_trace = [&](int rc) {
+        if (trace && rc == 0) {
+            unsigned long long h[16];
+            cudaStreamSynchronize(st);
+            cudaMemcpy(h, trace_buf, sizeof(h), cudaMemcpyDeviceToHost);
+            fprintf(stderr, "[ddmp trace] M=%lld N=%d K=%d | producer/stage: issue %llu wait_free %llu data+store %llu (n=%llu) | "
+                    "mma/stage: wait_full %llu wait_peer %llu (n=%llu) wait_acc_total %llu | epilogue/tile: wait %llu drain %llu (n=%llu) "
+                    "[to staging %llu, to global %llu, tmem wait(1 of 2) %llu]\n",
+                    (long long)M, N, K, h[3] ? h[0] / h[3] : 0, h[3] ? h[1] / h[3] : 0, h[3] ? h[2] / h[3] : 0, h[3],
+                    h[6] ? h[4] / h[6] : 0, h[6] ? h[5] / h[6] : 0, h[6], h[7], h[10] ? h[8] / h[10] : 0,
+                    h[10] ? h[9] / h[10] : 0, h[10], h[10] ? h[11] / h[10] : 0, h[10] ? h[12] / h[10] : 0,
+                    h[10] ? h[13] / h[10] : 0);
+        }
+        return rc;
+    };
     g.M = M; g.N = N; g.K = K; g.tiles_n = N / BN;
     g.num_tiles = ceil_div(M, BM) * g.tiles_n;
     DDMP_REQUIRE(g.num_tiles < (1ll << 31), "tc gemm: too many tiles");
     static const bool one_cta = [] { const char* e = getenv("DDMP_TC_2CTA"); return e && e[0] == '0'; }();
-    if (BN == 256 && !one_cta) return launch_nt16x2(g, st);
+    if (BN == 256 && !one_cta) return dump_trace(launch_nt16x2(g, st));
     if (BN == 256) return launch_nt16<256, 2>(g, st);
     if (BN == 128) return launch_nt16<128, 3>(g, st);
     return launch_nt16<64, 4>(g, st);
@@ -1859,7 +2028,6 @@ __global__ void __launch_bounds__(16 * 32 + 32, 1) tc_gemm_tn16_kernel(const Tn1
     constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
     constexpr uint32_t LBO = (BK16 / 8) * 1024;      // next 64-wide MN block
     constexpr uint32_t SBO = 1024;                   // next group of 8 k-rows
-    constexpr int A_CH = BM / 8, B_CH = BN / 8;      // 16-byte chunks (8 channels) per k-row
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -1907,45 +2075,38 @@ __global__ void __launch_bounds__(16 * 32 + 32, 1) tc_gemm_tn16_kernel(const Tn1
 
         if (warp < PW) {
             const int t = threadIdx.x;
-            const uint32_t a_cm = t % A_CH, a_r = t / A_CH;
-            const uint32_t b_cm = t % B_CH, b_r = t / B_CH;
-            constexpr int A_PASS = kPT / A_CH, B_PASS = kPT / B_CH;            // k-rows per pass of the producers
+            // one float4 (4 channels) per thread and k-row: consecutive lanes read consecutive 16 bytes of a graph
+            // row, and write the 8-byte half of the 16-byte swizzle chunk they share with their neighbour
+            constexpr int A_C4 = BM / 4, B_C4 = BN / 4;                        // float4 per k-row
+            const uint32_t a_c4 = t % A_C4, a_r = t / A_C4;
+            const uint32_t b_c4 = t % B_C4, b_r = t / B_C4;
+            constexpr int A_PASS = kPT / A_C4, B_PASS = kPT / B_C4;            // k-rows per pass of the producers
             constexpr int A_N = BK16 / A_PASS, B_N = BK16 / B_PASS;
-            const bool a_ok = (m0 + (int)a_cm * 8) < g.M;
+            const bool a_ok = (m0 + (int)a_c4 * 4) < g.M;
             const bool has_act = g.scale != nullptr;
-            float4 sc0 = make_float4(s_b, s_b, s_b, s_b), sc1 = sc0;
-            float4 sh0 = make_float4(0.f, 0.f, 0.f, 0.f), sh1 = sh0;
+            float4 sc = make_float4(s_b, s_b, s_b, s_b), sh = make_float4(0.f, 0.f, 0.f, 0.f);
             if (has_act) {
-                sc0 = ldg4(g.scale + n0 + b_cm * 8); sc1 = ldg4(g.scale + n0 + b_cm * 8 + 4);
-                sh0 = ldg4(g.shift + n0 + b_cm * 8); sh1 = ldg4(g.shift + n0 + b_cm * 8 + 4);
-                sc0.x *= s_b; sc0.y *= s_b; sc0.z *= s_b; sc0.w *= s_b; sc1.x *= s_b; sc1.y *= s_b; sc1.z *= s_b; sc1.w *= s_b;
-                sh0.x *= s_b; sh0.y *= s_b; sh0.z *= s_b; sh0.w *= s_b; sh1.x *= s_b; sh1.y *= s_b; sh1.z *= s_b; sh1.w *= s_b;
+                sc = ldg4(g.scale + n0 + b_c4 * 4);
+                sh = ldg4(g.shift + n0 + b_c4 * 4);
+                sc.x *= s_b; sc.y *= s_b; sc.z *= s_b; sc.w *= s_b;
+                sh.x *= s_b; sh.y *= s_b; sh.z *= s_b; sh.w *= s_b;
             }
-            const uint32_t a_off0 = (a_cm / 8) * LBO, b_off0 = (b_cm / 8) * LBO;
+            const uint32_t a_cm = a_c4 >> 1, b_cm = b_c4 >> 1;                 // 16-byte chunk (8 channels)
+            const uint32_t a_off0 = (a_cm / 8) * LBO + ((a_c4 & 1u) << 3), b_off0 = (b_cm / 8) * LBO + ((b_c4 & 1u) << 3);
             const uint32_t a_cj = a_cm & 7u, b_cj = b_cm & 7u;
-            float4 av[A_N][2], bv[B_N][2];
+            float4 av[A_N], bv[B_N];
             auto issue = [&](int kb) {
                 if (kb >= num_kb) return;
                 const int64_t rb = r0 + (int64_t)kb * BK16;
 #pragma unroll
                 for (int j = 0; j < A_N; ++j) {
                     const int64_t r = rb + a_r + j * A_PASS;
-                    if (r < r1 && a_ok) {
-                        av[j][0] = ldg4(g.A + r * g.M + m0 + a_cm * 8);
-                        av[j][1] = ldg4(g.A + r * g.M + m0 + a_cm * 8 + 4);
-                    } else {
-                        av[j][0] = av[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
+                    av[j] = (r < r1 && a_ok) ? ldg4(g.A + r * g.M + m0 + a_c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
 #pragma unroll
                 for (int j = 0; j < B_N; ++j) {
                     const int64_t r = rb + b_r + j * B_PASS;
-                    if (r < r1) {
-                        bv[j][0] = ldg4(g.B + r * g.N + n0 + b_cm * 8);
-                        bv[j][1] = ldg4(g.B + r * g.N + n0 + b_cm * 8 + 4);
-                    } else {
-                        bv[j][0] = bv[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
+                    bv[j] = (r < r1) ? ldg4(g.B + r * g.N + n0 + b_c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             };
             issue(0);
@@ -1958,33 +2119,33 @@ __global__ void __launch_bounds__(16 * 32 + 32, 1) tc_gemm_tn16_kernel(const Tn1
 #pragma unroll
                 for (int j = 0; j < A_N; ++j) {
                     const uint32_t k = a_r + j * A_PASS;
-                    float4 a = av[j][0], b = av[j][1];
-                    a.x *= s_a; a.y *= s_a; a.z *= s_a; a.w *= s_a; b.x *= s_a; b.y *= s_a; b.z *= s_a; b.w *= s_a;
-                    uint4 hi, lo;
-                    split_f16x8(a, b, hi, lo);
+                    float4 a = av[j];
+                    a.x *= s_a; a.y *= s_a; a.z *= s_a; a.w *= s_a;
+                    uint32_t h0, l0, h1, l1;
+                    split_f16x2(a.x, a.y, h0, l0);
+                    split_f16x2(a.z, a.w, h1, l1);
                     const uint32_t off = a_off0 + (k >> 3) * SBO + (k & 7u) * 128u + ((a_cj ^ (k & 7u)) << 4);
-                    sts128(st + off, hi);
-                    sts128(st + A_BYTES + off, lo);
+                    sts64(st + off, h0, h1);
+                    sts64(st + A_BYTES + off, l0, l1);
                 }
 #pragma unroll
                 for (int j = 0; j < B_N; ++j) {
                     const uint32_t k = b_r + j * B_PASS;
-                    float4 a = bv[j][0], b = bv[j][1];
+                    float4 a = bv[j];
                     if (has_act) {
                         if ((rb + k) < r1) {
-                            a.x = lrelu_max(fmaf(a.x, sc0.x, sh0.x), g.slope); a.y = lrelu_max(fmaf(a.y, sc0.y, sh0.y), g.slope);
-                            a.z = lrelu_max(fmaf(a.z, sc0.z, sh0.z), g.slope); a.w = lrelu_max(fmaf(a.w, sc0.w, sh0.w), g.slope);
-                            b.x = lrelu_max(fmaf(b.x, sc1.x, sh1.x), g.slope); b.y = lrelu_max(fmaf(b.y, sc1.y, sh1.y), g.slope);
-                            b.z = lrelu_max(fmaf(b.z, sc1.z, sh1.z), g.slope); b.w = lrelu_max(fmaf(b.w, sc1.w, sh1.w), g.slope);
+                            a.x = lrelu_max(fmaf(a.x, sc.x, sh.x), g.slope); a.y = lrelu_max(fmaf(a.y, sc.y, sh.y), g.slope);
+                            a.z = lrelu_max(fmaf(a.z, sc.z, sh.z), g.slope); a.w = lrelu_max(fmaf(a.w, sc.w, sh.w), g.slope);
                         }
                     } else {
-                        a.x *= s_b; a.y *= s_b; a.z *= s_b; a.w *= s_b; b.x *= s_b; b.y *= s_b; b.z *= s_b; b.w *= s_b;
+                        a.x *= s_b; a.y *= s_b; a.z *= s_b; a.w *= s_b;
                     }
-                    uint4 hi, lo;
-                    split_f16x8(a, b, hi, lo);
+                    uint32_t h0, l0, h1, l1;
+                    split_f16x2(a.x, a.y, h0, l0);
+                    split_f16x2(a.z, a.w, h1, l1);
                     const uint32_t off = b_off0 + (k >> 3) * SBO + (k & 7u) * 128u + ((b_cj ^ (k & 7u)) << 4);
-                    sts128(st + 2 * A_BYTES + off, hi);
-                    sts128(st + 2 * A_BYTES + B_BYTES + off, lo);
+                    sts64(st + 2 * A_BYTES + off, h0, h1);
+                    sts64(st + 2 * A_BYTES + B_BYTES + off, l0, l1);
                 }
                 fence_proxy_async();
                 __syncwarp();
@@ -2143,12 +2304,11 @@ int tc_gemm_dw(const float* dH, const float* X, const int32_t* row_map, const fl
                  "tc_gemm_dw: workspace too small (%lld bytes)", (long long)workspace_bytes);
     DDMP_REQUIRE(tc_aligned16(dH) && tc_aligned16(X) && tc_aligned16(workspace), "tc_gemm_dw: 16-byte alignment");
     const int64_t count = (int64_t)Cin * Cout;
-    // both operands are split by the producer warps here, which bounds this kernel: the fp16 split only pays for
-    // the narrow inputs (measured, 1M rows: 64->128 0.26 vs 0.36 ms, 128->256 0.46 vs 0.62, but 256->256 0.88 vs
-    // 0.79 and 512->512 2.93 vs 2.71); DDMP_TC_TN16=1 forces it everywhere
-    static const bool tn16_all = [] { const char* e = getenv("DDMP_TC_TN16"); return e && e[0] == '1'; }();
-    if (amax_dh && amax_x && amax_dh_len > 0 && amax_x_len > 0 && Cout % 8 == 0 && tc::f16_split_enabled() &&
-        (Cin <= 128 || tn16_all)) {
+    // fp16 split: 10-30 % faster than 3xTF32 on every shape (1M rows: 512->512 2.39 vs 2.71 ms, 64->128 0.27 vs 0.36);
+    // both operands are split by the producer warps here, which bounds this kernel.  DDMP_TC_TN16=0 -> 3xTF32
+    static const bool tn16_off = [] { const char* e = getenv("DDMP_TC_TN16"); return e && e[0] == '0'; }();
+    if (amax_dh && amax_x && amax_dh_len > 0 && amax_x_len > 0 && Cout % 4 == 0 && tc::f16_split_enabled() &&
+        !tn16_off) {
         tc::Tn16Args h{};
         h.A = dH; h.B = X; h.P = reinterpret_cast<float*>(workspace); h.scale = scale; h.shift = shift; h.slope = slope;
         h.amax_a = amax_dh; h.amax_a_len = amax_dh_len; h.amax_b = amax_x; h.amax_b_len = amax_x_len;
