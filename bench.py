@@ -351,7 +351,7 @@ def run_ours(args):
     tc_tflops = tc_flop / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
     out["roofline_tensor"] = {
         "bound": "tensor", "kernel": "tc_gemm_nt16x2/nt16 (tcgen05 kind::f16, fp32 emulated with 3 fp16 MMAs: X.W^T and "
-                                     "dH.W; tc_gemm_tn16: dH^T.X); all dense transforms of width >= 64",
+                                     "dH.W; tc_gemm_tn16x2/tn16: dH^T.X); all dense transforms of width >= 64",
         "achieved": tc_tflops, "unit": "TFLOP/s", "peak": bf16_sus, "frac": tc_tflops / bf16_sus,
         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS bf16, kernel timed inside a long step)",
         "achieved_counts": "ALGORITHMIC fp32 flops 2*rows*Cin*Cout; an fp32 product costs 3 MMAs, so the ceiling "

@@ -2229,6 +2229,249 @@ static int launch_tn16(const Tn16Args& g, cudaStream_t st) {
     return check_launch("tc_gemm_tn16");
 }
 
+// TN kernel on CTA pairs (cta_group::2): the pair owns a 256 x (256*NACC) tile of dW.  Each CTA splits its 128
+// channels of dH and 128*NACC channels of X per k-row, the MMAs (M = 256, N = 256 per accumulator) read both CTAs'
+// halves, and each CTA's TMEM receives its 128 output rows x 256*NACC columns.  Against the single-CTA kernel
+// (128 x 256 tiles) every element of dH is split once instead of Cin/256 times and every element of X Cout/256
+// instead of Cout/128 times: the producer work per MMA -- which bounds this kernel -- halves for 512 x 512.
+template <int NACC>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(16 * 32 + 32, 1) tc_gemm_tn16x2_kernel(const Tn16Args g) {
+    constexpr int PW = 16;
+    constexpr int kPT = PW * 32;
+    constexpr int STAGES = (NACC == 2) ? 2 : 3;
+    constexpr uint32_t A_BYTES = BM * BK16 * 2;          // this CTA's 128 dH channels x 64 k-rows, one of hi / lo
+    constexpr uint32_t B_BLK = 128 * BK16 * 2;           // this CTA's 128 X channels of one accumulator
+    constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + NACC * 2 * B_BLK;
+    constexpr uint32_t TMEM_COLS = NACC * 256;
+    constexpr uint32_t LBO = (BK16 / 8) * 1024;
+    constexpr uint32_t SBO = 1024;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* peer_ready = empty_bar + STAGES;           // leader only
+    uint64_t* accum_bar = peer_ready + STAGES;
+    uint64_t* drained_bar = accum_bar + 1;               // leader only: both CTAs have read the accumulators out
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(drained_bar + 1);
+    uint32_t* amax_slot = tmem_slot + 1;                 // [2]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int64_t num_pairs = gridDim.x / 2, pair = blockIdx.x / 2;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar + s, PW);
+            mbar_init(empty_bar + s, 1);
+            mbar_init(peer_ready + s, 1);
+        }
+        mbar_init(accum_bar, 1);
+        mbar_init(drained_bar, 2 * PW);
+        amax_slot[0] = 0u;
+        amax_slot[1] = 0u;
+        fence_barrier_init();
+    }
+    cluster_sync_all();
+    if (warp == PW) tmem_alloc_2cta(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    block_amax_bits(g.amax_a, g.amax_a_len, amax_slot);
+    block_amax_bits(g.amax_b, g.amax_b_len, amax_slot + 1);
+    __syncthreads();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t smem_base = smem_u32(smem);
+    float s_a, inv_sa, s_b, inv_sb;
+    scale_from_bits(amax_slot[0], s_a, inv_sa);
+    scale_from_bits(amax_slot[1], s_b, inv_sb);
+    const int tiles = g.tiles_m * g.tiles_n;             // pair tiles: 256 x (256*NACC)
+
+    uint32_t it = 0;
+    uint32_t item_no = 0;
+    for (int64_t item = pair; item < g.num_items; item += num_pairs, ++item_no) {
+        const int tile = (int)(item % tiles);
+        const int64_t seg = item / tiles;
+        const int m0 = (tile / g.tiles_n) * 256 + (int)rank * 128;     // this CTA's dH channels / output rows
+        const int n0 = (tile % g.tiles_n) * 256 * NACC;                // first column of the pair tile
+        const int64_t r0 = seg * kSegRows;
+        const int64_t r1 = (r0 + kSegRows < g.rows) ? (r0 + kSegRows) : g.rows;
+        const int num_kb = (int)((r1 - r0 + BK16 - 1) / BK16);
+
+        if (warp < PW) {
+            const int t = threadIdx.x;
+            constexpr int A_C4 = 32, B_C4 = NACC * 32;                         // float4 per k-row (this CTA's part)
+            const uint32_t a_c4 = t % A_C4, a_r = t / A_C4;
+            const uint32_t b_c4 = t % B_C4, b_r = t / B_C4;
+            constexpr int A_PASS = kPT / A_C4, B_PASS = kPT / B_C4;
+            constexpr int A_N = BK16 / A_PASS, B_N = BK16 / B_PASS;
+            const uint32_t b_acc = b_c4 / 32, b_in = b_c4 % 32;                // accumulator block, float4 inside it
+            const int b_ch = n0 + (int)b_acc * 256 + (int)rank * 128 + (int)b_in * 4;   // global X channel
+            const bool has_act = g.scale != nullptr;
+            float4 sc = make_float4(s_b, s_b, s_b, s_b), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (has_act) {
+                sc = ldg4(g.scale + b_ch);
+                sh = ldg4(g.shift + b_ch);
+                sc.x *= s_b; sc.y *= s_b; sc.z *= s_b; sc.w *= s_b;
+                sh.x *= s_b; sh.y *= s_b; sh.z *= s_b; sh.w *= s_b;
+            }
+            const uint32_t a_cm = a_c4 >> 1, b_cm = b_in >> 1;
+            const uint32_t a_off0 = (a_cm / 8) * LBO + ((a_c4 & 1u) << 3);
+            const uint32_t b_off0 = 2 * A_BYTES + b_acc * (2 * B_BLK) + (b_cm / 8) * LBO + ((b_in & 1u) << 3);
+            const uint32_t a_cj = a_cm & 7u, b_cj = b_cm & 7u;
+            float4 av[A_N], bv[B_N];
+            auto issue = [&](int kb) {
+                if (kb >= num_kb) return;
+                const int64_t rb = r0 + (int64_t)kb * BK16;
+#pragma unroll
+                for (int j = 0; j < A_N; ++j) {
+                    const int64_t r = rb + a_r + j * A_PASS;
+                    av[j] = (r < r1) ? ldg4(g.A + r * g.M + m0 + a_c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int j = 0; j < B_N; ++j) {
+                    const int64_t r = rb + b_r + j * B_PASS;
+                    bv[j] = (r < r1) ? ldg4(g.B + r * g.N + b_ch) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            };
+            issue(0);
+            for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                const int64_t rb = r0 + (int64_t)kb * BK16;
+                mbar_wait_cluster(empty_bar + s, ph ^ 1u);
+                const uint32_t st = smem_base + s * STAGE_BYTES;
+#pragma unroll
+                for (int j = 0; j < A_N; ++j) {
+                    const uint32_t k = a_r + j * A_PASS;
+                    float4 a = av[j];
+                    a.x *= s_a; a.y *= s_a; a.z *= s_a; a.w *= s_a;
+                    uint32_t h0, l0, h1, l1;
+                    split_f16x2(a.x, a.y, h0, l0);
+                    split_f16x2(a.z, a.w, h1, l1);
+                    const uint32_t off = a_off0 + (k >> 3) * SBO + (k & 7u) * 128u + ((a_cj ^ (k & 7u)) << 4);
+                    sts64(st + off, h0, h1);
+                    sts64(st + A_BYTES + off, l0, l1);
+                }
+#pragma unroll
+                for (int j = 0; j < B_N; ++j) {
+                    const uint32_t k = b_r + j * B_PASS;
+                    float4 a = bv[j];
+                    if (has_act) {
+                        if ((rb + k) < r1) {
+                            a.x = lrelu_max(fmaf(a.x, sc.x, sh.x), g.slope); a.y = lrelu_max(fmaf(a.y, sc.y, sh.y), g.slope);
+                            a.z = lrelu_max(fmaf(a.z, sc.z, sh.z), g.slope); a.w = lrelu_max(fmaf(a.w, sc.w, sh.w), g.slope);
+                        }
+                    } else {
+                        a.x *= s_b; a.y *= s_b; a.z *= s_b; a.w *= s_b;
+                    }
+                    uint32_t h0, l0, h1, l1;
+                    split_f16x2(a.x, a.y, h0, l0);
+                    split_f16x2(a.z, a.w, h1, l1);
+                    const uint32_t off = b_off0 + (k >> 3) * SBO + (k & 7u) * 128u + ((b_cj ^ (k & 7u)) << 4);
+                    sts64(st + off, h0, h1);
+                    sts64(st + B_BLK + off, l0, l1);
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full_bar + s);
+                issue(kb + 1);
+            }
+            // ---- epilogue of this item: this CTA's 128 rows x 256*NACC columns ----
+            mbar_wait_cluster(accum_bar, item_no & 1u);
+            tc_fence_after();
+            constexpr int PARTS = PW / 4;
+            constexpr int CPART = (256 * NACC) / PARTS;
+            const int q = warp & 3, part = warp >> 2;
+            const int m = m0 + q * 32 + lane;
+            float* prow = g.P + (seg * g.M + m) * (int64_t)g.N + n0;
+            const float inv = inv_sa * inv_sb;
+#pragma unroll 1
+            for (int cb = part * CPART; cb < (part + 1) * CPART; cb += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, v);
+                if (m < g.M) {
+#pragma unroll
+                    for (int e = 0; e < 32; e += 4)
+                        st4(prow + cb + e, make_float4(__uint_as_float(v[e]) * inv, __uint_as_float(v[e + 1]) * inv,
+                                                       __uint_as_float(v[e + 2]) * inv, __uint_as_float(v[e + 3]) * inv));
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (rank == 0) mbar_arrive(drained_bar);
+                else mbar_arrive_remote(drained_bar, 0);
+            }
+        } else {
+            if (lane == 0) {
+                if (rank == 0) {
+                    constexpr uint32_t idesc = make_idesc16(256, 256, true, true);
+                    if (item_no > 0) {
+                        mbar_wait_cluster(drained_bar, (item_no - 1) & 1u);
+                        tc_fence_after();
+                    }
+                    for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                        const int s = it % STAGES;
+                        const uint32_t ph = (it / STAGES) & 1;
+                        mbar_wait(full_bar + s, ph);
+                        mbar_wait_cluster(peer_ready + s, ph);
+                        tc_fence_after();
+                        const uint32_t sa = smem_base + s * STAGE_BYTES;
+#pragma unroll
+                        for (int ks = 0; ks < BK16 / UMMA_K16; ++ks) {
+                            const uint32_t koff = ks * 2u * SBO;
+                            const uint64_t a_hi = make_desc(sa + koff, LBO, SBO, 2);
+                            const uint64_t a_lo = make_desc(sa + A_BYTES + koff, LBO, SBO, 2);
+#pragma unroll
+                            for (int j = 0; j < NACC; ++j) {
+                                const uint32_t sb = sa + 2 * A_BYTES + j * (2 * B_BLK) + koff;
+                                const uint64_t b_hi = make_desc(sb, LBO, SBO, 2);
+                                const uint64_t b_lo = make_desc(sb + B_BLK, LBO, SBO, 2);
+                                const uint32_t d = tmem_base + j * 256;
+                                umma_f16_2cta(d, a_lo, b_hi, idesc, (kb | ks) != 0);
+                                umma_f16_2cta(d, a_hi, b_lo, idesc, 1);
+                                umma_f16_2cta(d, a_hi, b_hi, idesc, 1);
+                            }
+                        }
+                        umma_commit_2cta(empty_bar + s);
+                    }
+                    umma_commit_2cta(accum_bar);
+                } else {
+                    for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                        const int s = it % STAGES;
+                        const uint32_t ph = (it / STAGES) & 1;
+                        mbar_wait(full_bar + s, ph);
+                        mbar_arrive_remote(peer_ready + s, 0);
+                    }
+                }
+            } else {
+                it += num_kb;
+            }
+            __syncwarp();
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == PW) {
+        tc_fence_after();
+        tmem_dealloc_2cta(tmem_base, TMEM_COLS);
+    }
+}
+
+template <int NACC>
+static int launch_tn16x2(const Tn16Args& g, cudaStream_t st) {
+    constexpr int STAGES = (NACC == 2) ? 2 : 3;
+    constexpr size_t smem = (size_t)STAGES * (2 * BM * BK16 * 2 + NACC * 2 * 128 * BK16 * 2) + 1024 + 256;
+    static bool configured = false;
+    if (!configured) {
+        DDMP_CUDA(cudaFuncSetAttribute(tc_gemm_tn16x2_kernel<NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+        configured = true;
+    }
+    const int64_t pairs = g.num_items < kNumSMs / 2 ? g.num_items : kNumSMs / 2;
+    tc_gemm_tn16x2_kernel<NACC><<<(unsigned)(2 * pairs), 16 * 32 + 32, smem, st>>>(g);
+    return check_launch("tc_gemm_tn16x2");
+}
+
 __global__ void transpose_kernel(const float* __restrict__ W, float* __restrict__ Wt, int rows, int cols) {
     __shared__ float tile[32][33];
     const int x = blockIdx.x * 32 + threadIdx.x, y0 = blockIdx.y * 32;
@@ -2316,7 +2559,13 @@ int tc_gemm_dw(const float* dH, const float* X, const int32_t* row_map, const fl
         h.tiles_m = (int)ceil_div(Cout, tc::BM);
         const int64_t segs16 = ceil_div(n, tc::kSegRows);
         int rc16;
-        if (Cin % 256 == 0) { h.tiles_n = Cin / 256; h.num_items = segs16 * h.tiles_m * h.tiles_n; rc16 = tc::launch_tn16<256, 2>(h, st); }
+        static const bool tn_one_cta = [] { const char* e = getenv("DDMP_TC_2CTA"); return e && e[0] == '0'; }();
+        if (!tn_one_cta && Cout % 256 == 0 && Cin % 256 == 0) {
+            h.tiles_m = Cout / 256;
+            if (Cin % 512 == 0) { h.tiles_n = Cin / 512; h.num_items = segs16 * h.tiles_m * h.tiles_n; rc16 = tc::launch_tn16x2<2>(h, st); }
+            else { h.tiles_n = Cin / 256; h.num_items = segs16 * h.tiles_m * h.tiles_n; rc16 = tc::launch_tn16x2<1>(h, st); }
+        }
+        else if (Cin % 256 == 0) { h.tiles_n = Cin / 256; h.num_items = segs16 * h.tiles_m * h.tiles_n; rc16 = tc::launch_tn16<256, 2>(h, st); }
         else if (Cin % 128 == 0) { h.tiles_n = Cin / 128; h.num_items = segs16 * h.tiles_m * h.tiles_n; rc16 = tc::launch_tn16<128, 3>(h, st); }
         else { h.tiles_n = Cin / 64; h.num_items = segs16 * h.tiles_m * h.tiles_n; rc16 = tc::launch_tn16<64, 4>(h, st); }
         if (rc16) return rc16;
