@@ -1063,7 +1063,7 @@ struct Nt16Args {
     const float* amax;       // bound of |act(A)|: max over this array
     int64_t amax_len;
     unsigned long long* trace;   // profiling only (DDMP_TC_TRACE=1): per-role cycle counters of CTA 0
-    int flags;               // bit 0: prefetch the next tile's A rows into L2
+    int flags;               // DDMP_TC_F16_FLAGS. bit 0: prefetch the next tile's A rows into L2; bit 3: unstaged epilogue
     int64_t M;
     int N, K;
     int tiles_n;
@@ -1276,17 +1276,26 @@ template <class Args>
 __device__ __forceinline__ void epilogue_block32(const Args& g, uint32_t (&v)[32], float inv_sa, uint32_t stg, int lane,
                                                  int64_t mrow0, int ncol0) {
     const int cc = lane & 7;
-    const bool tr = g.trace && blockIdx.x == 0 && threadIdx.x == 12 * 32;
-    long long p0 = 0, p1 = 0, p2 = 0;
-    if (tr) p0 = clock64();
     float4 w = ldg4(g.inv_sw + ncol0 + cc * 4);          // scales of the 4 columns this lane stores
+    if (g.flags & 8) {                                   // A/B switch: no staging, thread-per-row 16-byte stores (slower)
+        const int64_t m = mrow0 + lane;
+        if (m < g.M) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float4 ws = ldg4(g.inv_sw + ncol0 + 4 * i);
+                st4(g.C + m * g.N + ncol0 + 4 * i,
+                    make_float4(__uint_as_float(v[4 * i]) * inv_sa * ws.x, __uint_as_float(v[4 * i + 1]) * inv_sa * ws.y,
+                                __uint_as_float(v[4 * i + 2]) * inv_sa * ws.z, __uint_as_float(v[4 * i + 3]) * inv_sa * ws.w));
+            }
+        }
+        return;
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i)              // row = lane, 16-byte chunk i -> swizzled chunk i ^ (lane & 7)
         sts128(stg + (uint32_t)lane * 128u + (uint32_t)((i ^ (lane & 7)) << 4),
                make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
     w.x *= inv_sa; w.y *= inv_sa; w.z *= inv_sa; w.w *= inv_sa;
     __syncwarp();
-    if (tr) p1 = clock64();
     uint4 o[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -1300,15 +1309,10 @@ __device__ __forceinline__ void epilogue_block32(const Args& g, uint32_t (&v)[32
         const int64_t m = mrow0 + j * 4 + (lane >> 3);
         if (m < g.M)
             st4(g.C + m * g.N + ncol0 + cc * 4,
-                make_float4(__uint_as_float(o[j].x) * w.x, __uint_as_float(o[j].y) * w.y, __uint_as_float(o[j].z) * w.z,
-                            __uint_as_float(o[j].w) * w.w));
+                make_float4(__uint_as_float(o[j].x) * w.x, __uint_as_float(o[j].y) * w.y,
+                            __uint_as_float(o[j].z) * w.z, __uint_as_float(o[j].w) * w.w));
     }
     __syncwarp();
-    if (tr) {
-        p2 = clock64();
-        g.trace[11] += (unsigned long long)(p1 - p0);    // registers -> staging
-        g.trace[12] += (unsigned long long)(p2 - p1);    // staging -> global
-    }
 }
 // taddr = TMEM address of (this warp's lane quarter, first column of the accumulator buffer)
 template <int BN, class Args>
