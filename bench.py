@@ -502,7 +502,7 @@ def run_partitioned(args):
                                       f"BatchNorm-statistic and weight-gradient all-reduce, replicated losses",
                           "faces": F, "vertices": V, "mode": "partition", "rank0_partition": halo,
                           "rank0_peak_mem_GiB": round(mem, 2)},
-               "e2e": None, "loss": float(loss), "clocks": sampler.summary()}
+               "e2e": None, "loss": float(loss.detach()), "clocks": sampler.summary()}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
