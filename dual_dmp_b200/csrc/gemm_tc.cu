@@ -1227,7 +1227,10 @@ __device__ __forceinline__ void produce_loop_simple(const Args& g, int64_t first
             sts64(st + off, h0, h1);
             sts64(st + a_bytes + off, l0, l1);
         }
+        long long cA = 0, cB = 0;
+        if (tr) cA = clock64();
         fence_proxy_async();
+        if (tr) cB = clock64();
         __syncwarp();
         if (tr) c3 = clock64();
         if (lane == 0) mbar_arrive(full_bar + s);
@@ -1235,6 +1238,8 @@ __device__ __forceinline__ void produce_loop_simple(const Args& g, int64_t first
             g.trace[1] += (unsigned long long)(c2 - c1);     // wait for a free stage
             g.trace[2] += (unsigned long long)(c3 - c2);     // wait for data + transform + stores + fence
             g.trace[3] += 1ull;
+            g.trace[14] += (unsigned long long)(cA - c2);    // ... of which: data wait + transform + store issue
+            g.trace[15] += (unsigned long long)(cB - cA);    // ... fence.proxy.async
         }
     };
     float4 buf0[NJ], buf1[NJ];
@@ -1748,11 +1753,11 @@ static int run_nt16(const float* A, const int* a_map, const float* scale, const 
             cudaMemcpy(h, trace_buf, sizeof(h), cudaMemcpyDeviceToHost);
             fprintf(stderr, "[ddmp trace] M=%lld N=%d K=%d | producer/stage: issue %llu wait_free %llu data+store %llu (n=%llu) | "
                     "mma/stage: wait_full %llu wait_peer %llu (n=%llu) wait_acc_total %llu | epilogue/tile: wait %llu drain %llu (n=%llu) "
-                    "[to staging %llu, to global %llu, tmem wait(1 of 2) %llu]\n",
+                    "[to staging %llu, to global %llu, tmem wait(1 of 2) %llu] producer detail: transform+stores %llu fence %llu\n",
                     (long long)M, N, K, h[3] ? h[0] / h[3] : 0, h[3] ? h[1] / h[3] : 0, h[3] ? h[2] / h[3] : 0, h[3],
                     h[6] ? h[4] / h[6] : 0, h[6] ? h[5] / h[6] : 0, h[6], h[7], h[10] ? h[8] / h[10] : 0,
                     h[10] ? h[9] / h[10] : 0, h[10], h[10] ? h[11] / h[10] : 0, h[10] ? h[12] / h[10] : 0,
-                    h[10] ? h[13] / h[10] : 0);
+                    h[10] ? h[13] / h[10] : 0, h[3] ? h[14] / h[3] : 0, h[3] ? h[15] / h[3] : 0);
         }
         return rc;
     };
