@@ -1,15 +1,19 @@
-// Dense feature transform on the 5th-generation tensor cores (DDMP_GEMM_TC): tcgen05.mma kind::tf32 with an
-// error-compensated 3xTF32 split (hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM), so the result keeps fp32-level
-// accuracy (the 1e-4 parity contract rules out plain TF32, SURVEY.md §7 hard part 1).
+// Dense feature transform on the 5th-generation tensor cores (DDMP_GEMM_TC): fp32 products emulated with three MMAs
+// on error-compensated operand splits, fp32 accumulation in TMEM (the 1e-4 parity contract rules out plain TF32 /
+// fp16, SURVEY.md §7 hard part 1).  Two splits:
+//   * fp16 (kind::f16, default when the caller supplies operand bounds): s*x = hi + lo in fp16, operands scaled by
+//     powers of two from device-side bounds -- section "fp32 emulation with three fp16 MMAs" below;
+//   * TF32 (kind::tf32): x = hi + lo in TF32, no range restriction, half the MMA rate.
 //
-//   NT kernel (xw, dx):  C[M=rows, N] = act(A)[rows, K] * B[N, K]^T        A, B K-major
-//   TN kernel (dw)    :  C[M, N] = sum_rows A[rows, M]^T * act(B)[rows, N]  A, B MN-major, split-K over rows
+//   NT kernels (xw, dx):  C[M=rows, N] = act(A)[rows, K] * B[N, K]^T        A, B K-major
+//   TN kernels (dw)    :  C[M, N] = sum_rows A[rows, M]^T * act(B)[rows, N]  A, B MN-major, split-K over rows
 //
-// The A/B operands cannot come straight from TMA: the activation (previous layer's BatchNorm + LeakyReLU) and the
-// hi/lo split are applied while the tile is staged, so 8 producer warps do   ld.global -> transform -> st.shared
-// into the 128-byte-swizzled UMMA canonical layout, one elected thread of a 9th warp issues the MMAs, and all
-// producer warps drain the TMEM accumulator in the epilogue.  Pipeline: `full`/`empty` mbarriers per smem stage,
-// tcgen05.commit releases a stage / publishes the accumulator.
+// The activation operand cannot come straight from TMA: the previous layer's BatchNorm + LeakyReLU, the scale and
+// the hi/lo split are applied while the tile is staged, so producer warps do  ld.global -> transform -> st.shared
+// into the 128-byte-swizzled UMMA canonical layout; the (pre-split, pre-swizzled) weights arrive by cp.async.bulk.
+// One elected thread issues the MMAs; `full`/`empty` mbarriers per smem stage; tcgen05.commit releases a stage /
+// publishes the accumulator; dedicated warps drain the double-buffered TMEM accumulator.  CTA pairs (cta_group::2)
+// where the shapes allow.  Kernel inventory and measured behaviour: DESIGN.md §4.2, profiles/README.md.
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
@@ -1075,51 +1079,10 @@ struct Nt16Args {
 // earlier mapping gave every thread 8 consecutive k as two 16-byte loads: each warp load then touched eight
 // half-used lines and the LSU data pipe, at 77 % busy, bounded the kernel: ncu, profiles/).  A thread's 4 k values
 // become 8 bytes of hi and 8 bytes of lo; the pair of lanes that shares a 16-byte swizzle chunk writes its halves.
-// Loads first (so the wait for a free stage overlaps them), then transform + split + swizzled stores.
 constexpr int kProdNJ = BM * 16 / kProducerThreads;      // rows per thread per k-block (8)
 constexpr int kProdRPP = kProducerThreads / 16;          // rows covered by one pass of the producer threads (16)
 __device__ __forceinline__ void sts64(uint32_t saddr, uint32_t x, uint32_t y) {
     asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(saddr), "r"(x), "r"(y) : "memory");
-}
-template <class Args>
-__device__ __forceinline__ void produce_load(const Args& g, const int64_t (&src_row)[kProdNJ], int k0,
-                                             float4 (&av)[kProdNJ]) {
-#pragma unroll
-    for (int j = 0; j < kProdNJ; ++j)
-        av[j] = (src_row[j] >= 0) ? ldg4(g.A + src_row[j] * g.K + k0) : make_float4(0.f, 0.f, 0.f, 0.f);
-}
-template <class Args>
-__device__ __forceinline__ void produce_store(const Args& g, const int64_t (&src_row)[kProdNJ], int k0,
-                                              float4 (&av)[kProdNJ], float s_a, bool has_act, int t, uint32_t st,
-                                              uint32_t a_bytes) {
-    // the power-of-two operand scale is folded into the affine part (LeakyReLU is positively homogeneous)
-    float4 sc = make_float4(s_a, s_a, s_a, s_a), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (has_act) {
-        sc = ldg4(g.scale + k0);
-        sh = ldg4(g.shift + k0);
-        sc.x *= s_a; sc.y *= s_a; sc.z *= s_a; sc.w *= s_a;
-        sh.x *= s_a; sh.y *= s_a; sh.z *= s_a; sh.w *= s_a;
-    }
-    const uint32_t c4 = t & 15;                           // float4 index inside the row's 256 bytes
-#pragma unroll
-    for (int j = 0; j < kProdNJ; ++j) {
-        const uint32_t row = (t >> 4) + j * kProdRPP;
-        float4 a = av[j];
-        if (has_act) {
-            if (src_row[j] >= 0) {
-                a.x = lrelu_max(fmaf(a.x, sc.x, sh.x), g.slope); a.y = lrelu_max(fmaf(a.y, sc.y, sh.y), g.slope);
-                a.z = lrelu_max(fmaf(a.z, sc.z, sh.z), g.slope); a.w = lrelu_max(fmaf(a.w, sc.w, sh.w), g.slope);
-            }
-        } else {
-            a.x *= s_a; a.y *= s_a; a.z *= s_a; a.w *= s_a;
-        }
-        uint32_t h0, l0, h1, l1;
-        split_f16x2(a.x, a.y, h0, l0);
-        split_f16x2(a.z, a.w, h1, l1);
-        const uint32_t off = sw128(row, c4 >> 1) + ((c4 & 1u) << 3);
-        sts64(st + off, h0, h1);
-        sts64(st + a_bytes + off, l0, l1);
-    }
 }
 // A k-block touches 256 bytes of each of the tile's 128 rows (stride K*4), and the next 256 bytes of the same rows a
 // microsecond later: DRAM sees short scattered bursts (measured: every shape of the fp16-split kernel ran at
@@ -1147,7 +1110,7 @@ __device__ __forceinline__ float4 ldg4_pinned(const float* p) {
 // a free stage and 1600 between the wait and the arrive, most of it load latency, while the MMA thread waited
 // 1100 cycles per k-block for `full`.
 template <int STAGES, class Args, class WaitEmpty>
-__device__ __forceinline__ void produce_loop_simple(const Args& g, int64_t first_tile, int64_t tile_step, int64_t row_mul,
+__device__ __forceinline__ void produce_loop(const Args& g, int64_t first_tile, int64_t tile_step, int64_t row_mul,
                                                     int64_t row_add, int num_kb, float s_a, uint32_t smem_base,
                                                     uint32_t stage_bytes, uint32_t a_bytes, uint64_t* full_bar,
                                                     uint64_t* empty_bar, WaitEmpty wait_empty) {
@@ -1433,7 +1396,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) tc_gemm_nt16_kernel(const Nt16A
     if (warp < kProducerWarps) {
         // ===== A producers (see produce_loop) =====
         auto wait_empty = [](uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); };
-        produce_loop_simple<STAGES>(g, (int64_t)blockIdx.x, (int64_t)gridDim.x, (int64_t)BM, 0, num_kb, s_a,
+        produce_loop<STAGES>(g, (int64_t)blockIdx.x, (int64_t)gridDim.x, (int64_t)BM, 0, num_kb, s_a,
                                         smem_base, STAGE_BYTES, A_BYTES, full_bar, empty_bar, wait_empty);
     } else if (warp == 8) {
         // ===== MMA issuer =====
@@ -1592,7 +1555,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kV2Threads, 1) tc_ge
 
     if (warp < kProducerWarps) {
         auto wait_empty = [](uint64_t* bar, uint32_t parity) { mbar_wait_cluster(bar, parity); };
-        produce_loop_simple<STAGES>(g, pair, num_pairs, (int64_t)(2 * BM), (int64_t)rank * BM, num_kb, s_a,
+        produce_loop<STAGES>(g, pair, num_pairs, (int64_t)(2 * BM), (int64_t)rank * BM, num_kb, s_a,
                                         smem_base, STAGE_BYTES, A_BYTES, full_bar, empty_bar, wait_empty);
     } else if (warp == 8) {
         if (lane == 0) {
