@@ -76,6 +76,45 @@ def test_tc_and_ffma_gemm_agree_1m():
     assert e < 5e-5
 
 
+def test_f16_split_gemms_full_size_vs_float64():
+    """the fp16-split tensor-core GEMMs (CTA-pair kernels, the default of the training step) at the full benchmark
+    shape, 1,003,520 rows x 512 -> 512, with the operand bounds the step supplies: sampled rows of X.W^T and dH.W and
+    the whole of dH^T.X against float64, linearity in the weights, bitwise determinism"""
+    from dual_dmp_b200 import functional as F_
+    torch.manual_seed(2)
+    n, C = 1003520, 512
+    X = torch.randn(n, C, device=DEV)
+    W = torch.randn(C, C, device=DEV) / C ** 0.5
+    W2 = torch.randn(C, C, device=DEV) / C ** 0.5
+    dH = torch.randn(n, C, device=DEV) * 1e-6 * torch.exp(torch.randn(n, 1, device=DEV))      # gradient-like scales
+    gamma, beta = torch.rand(C, device=DEV) + 0.5, torch.randn(C, device=DEV) * 0.2
+    mean, var = X.mean(0), X.var(0, unbiased=False)
+    rstd = torch.rsqrt(var + 1e-5)
+    sc, sh = gamma * rstd, beta - mean * gamma * rstd
+    bound = gamma.abs() * (n - 1) ** 0.5 + beta.abs()                       # what ddmp_bn_stats_finalize emits
+    nblk = F_.num_row_blocks(n, C)                                          # what ddmp_spmm_gcn(amax_blocks) emits
+    rpb = -(-n // nblk)
+    blockmax = torch.nn.functional.pad(dH.abs().amax(1), (0, nblk * rpb - n)).view(nblk, rpb).amax(1).contiguous()
+    rows = torch.randint(0, n, (257,), device=DEV)
+    act = torch.nn.functional.leaky_relu(X[rows].double() * sc.double() + sh.double(), 0.01)
+    H = F_.gemm_xw(X, W, scale=sc, shift=sh, backend=2, amax=bound)
+    e_xw = rel_err(H[rows], act @ W.double().t())
+    gX = F_.gemm_dx(dH, W, backend=2, amax=blockmax)
+    e_dx = rel_err(gX[rows], dH[rows].double() @ W.double())
+    dW = F_.gemm_dw(dH, X, C, scale=sc, shift=sh, backend=2, amax_dh=blockmax, amax_x=bound)
+    ref = torch.zeros(C, C, dtype=torch.float64, device=DEV)
+    for lo in range(0, n, 131072):                                          # float64 reference in slabs (memory)
+        a = torch.nn.functional.leaky_relu(X[lo:lo + 131072].double() * sc.double() + sh.double(), 0.01)
+        ref += dH[lo:lo + 131072].double().t() @ a
+    e_dw = rel_err(dW, ref)
+    e_lin = rel_err(F_.gemm_xw(X, W + W2, scale=sc, shift=sh, backend=2, amax=bound)[rows],
+                    H[rows].double() + F_.gemm_xw(X, W2, scale=sc, shift=sh, backend=2, amax=bound)[rows].double())
+    report("f16-split GEMMs 1M x 512x512 (xw, dx, dw, linearity)", (e_xw, e_dx, e_dw, e_lin))
+    assert e_xw < 5e-6 and e_dx < 5e-6 and e_dw < 2e-5 and e_lin < 5e-6, (e_xw, e_dx, e_dw, e_lin)
+    assert torch.equal(H, F_.gemm_xw(X, W, scale=sc, shift=sh, backend=2, amax=bound))
+    assert torch.equal(dW, F_.gemm_dw(dH, X, C, scale=sc, shift=sh, backend=2, amax_dh=blockmax, amax_x=bound))
+
+
 def test_network_equivariance_and_determinism_1m(big):
     """the Morton relabelling must not change the result (this is what legitimises the reorder); reruns are bitwise
     identical; outputs are finite and NormalNet rows are unit vectors"""
