@@ -21,8 +21,19 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
-# stdout carries the one JSON line only: NCCL's version banner / debug output goes to stderr
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
+
+def _claim_stdout():
+    """stdout must carry the one JSON line only, but libraries write to file descriptor 1 behind Python's back (NCCL
+    prints its version banner there).  Keep a private duplicate of the real stdout for the result line and point
+    descriptor 1 at stderr for everything else."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
+RESULT_OUT = _claim_stdout() if __name__ == "__main__" else sys.stdout
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
@@ -377,7 +388,7 @@ def run_ours(args):
                    for k_, v in by_width.items()}, open(args.detail, "w"), indent=1)
     if not args.no_cpu_baseline and world == 1:
         out["cpu_baseline"] = cpu_reference(args, steps=2, warmup=1, target_faces=F)
-    print(json.dumps(out), flush=True)
+    print(json.dumps(out), file=RESULT_OUT, flush=True)
     if dist is not None:
         dist.destroy_process_group()
 
@@ -429,7 +440,7 @@ def run_reference(args):
                                   f"bnfloop={args.bnfloop} (CPU: bounded sample, see cpu_baseline.sample)"},
            "cpu_baseline": base,
            "e2e": {"value": base["value"], "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out), flush=True)
+    print(json.dumps(out), file=RESULT_OUT, flush=True)
 
 
 def run_partitioned(args):
@@ -505,7 +516,7 @@ def run_partitioned(args):
                           "faces": F, "vertices": V, "mode": "partition", "rank0_partition": halo,
                           "rank0_peak_mem_GiB": round(mem, 2)},
                "e2e": None, "loss": float(loss.detach()), "clocks": sampler.summary()}
-        print(json.dumps(out), flush=True)
+        print(json.dumps(out), file=RESULT_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
