@@ -3,8 +3,14 @@
 PosNet + NormalNet forward, five losses, backward, clip, Adam; reference main.py:88-110 — at 1M faces).
 
   python bench.py --gpus N --steps K --warmup W            our arm   (libddmp_b200 CUDA kernels)
+        N = 1: one 1M-face mesh on one GPU (BASELINE.json configs[2], the metric's configuration).
+        N > 1: ONE mesh of N x 1M faces (icosphere n = round(224 sqrt N)) range-partitioned over the N GPUs with NCCL
+               halo exchange + BatchNorm / gradient all-reduce (configs[4]'s mechanism, weak scaling); value is in
+               1M-face-equivalent iters/s so the N = 1 point is the same quantity.  --mode independent = one mesh fit
+               per GPU (configs[3]'s mechanism), --mode partition --freq n = strong scaling on a fixed mesh.
   python bench.py --impl reference --gpus N ...            reference arm: the CPU oracle port of the reference's
-                                                           PyG path on the host cores, on a bounded sample
+                                                           PyG path on the host cores, timed on the SAME 1M-face mesh
+                                                           (as many whole steps as fit the time budget)
 
 One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for every field.
 """
@@ -53,14 +59,19 @@ def parse_args():
                     help="icosphere frequency: F = 20 n^2 (224 -> 1,003,520 faces); use --freq under torchrun")
     ap.add_argument("--bnfloop", type=int, default=1)
     ap.add_argument("--k", type=float, nargs=5, default=[3.0, 4.0, 4.0, 4.0, 1.0])
-    ap.add_argument("--cpu-n", type=int, default=40, help="icosphere frequency of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-n", type=int, default=None,
+                    help="icosphere frequency of the CPU arm's mesh (default: the benchmark mesh itself when host RAM "
+                         "allows, else the largest that fits, flagged as extrapolated)")
+    ap.add_argument("--cpu-budget-s", type=float, default=240.0, help="wall-clock budget of the reference arm's steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="run PosNet and NormalNet on one stream")
     ap.add_argument("--no-graph", action="store_true", help="time the eager drop-in step instead of the CUDA-graph one")
-    ap.add_argument("--mode", default="independent", choices=["independent", "partition"],
-                    help="N>1: 'independent' = one mesh fit per GPU (weak scaling, default); 'partition' = ONE mesh "
-                         "range-partitioned over the GPUs with NCCL halo exchange (strong scaling)")
+    ap.add_argument("--mode", default="auto", choices=["auto", "independent", "partition", "partition-weak"],
+                    help="auto: N=1 -> one mesh on one GPU; N>1 -> 'partition-weak' (one mesh of N x 1M faces "
+                         "range-partitioned over the GPUs, NCCL halo exchange; weak scaling).  'independent' = one mesh "
+                         "fit per GPU, no data-path collective.  'partition' = strong scaling on the --freq mesh")
+    ap.add_argument("--no-mode-a", action="store_true", help="N>1: skip the independent-replica side measurement")
     ap.add_argument("--detail", default=None, help="write a per-kernel-group timing table (JSON) to this path")
     return ap.parse_args()
 
@@ -80,6 +91,103 @@ def build_case(n):
 def spmm_bytes(n_nodes, nnz, C):
     """rowptr + col + w + read H once + write Y once."""
     return 4 * ((n_nodes + 1) + 2 * nnz + 2 * n_nodes * C)
+
+
+def _sha256(path):
+    import hashlib
+    return hashlib.sha256(open(path, "rb").read()).hexdigest()
+
+
+def spmm_traffic(args, n_sp, sp_bytes):
+    """DRAM traffic per SpMM launch (dram__bytes_read.sum + dram__bytes_write.sum, average over the 48 launches of a
+    step) from the committed ncu capture -- reported only when that capture was taken on the spmm.cu that is being
+    benchmarked (sha256 recorded by scripts/spmm_traffic.py) and on the benchmark mesh; otherwise null."""
+    path = os.path.join(ROOT, "profiles", "spmm_dram_traffic_r2.json")
+    try:
+        tj = json.load(open(path))
+    except Exception:
+        return None, "no ncu capture for this build (profiles/spmm_dram_traffic_r2.json missing)"
+    src = os.path.join(ROOT, "dual_dmp_b200", "csrc", "spmm.cu")
+    if tj.get("spmm_cu_sha256") != _sha256(src):
+        return None, "ncu capture is of an older spmm.cu (sha256 mismatch): traffic not reported"
+    if args.n != tj.get("n") or not n_sp:
+        return None, "ncu capture is of another mesh"
+    return tj["dram_bytes_per_launch_avg"], (
+        "dram__bytes_read.sum + dram__bytes_write.sum, average per launch over the %d launches of a step, ncu capture "
+        "%s of this spmm.cu; algorithmic average per launch = %.0f" % (tj.get("launches"), tj.get("source"),
+                                                                      sp_bytes / n_sp))
+
+
+def loss_bytes(V, F, E, bnfloop):
+    """SURVEY.md §8d algorithmic bytes of the loss phase, forward + backward (fp32 values, int32 indices)"""
+    fwd = (24 * V                              # pos_rec
+           + 24 * F                            # norm_rec
+           + 4 * (V + 1) + 4 * 2 * E + 24 * V  # uniform Laplacian over the vertex CSR
+           + 12 * F + 12 * V + 12 * F          # pos_norm: faces + pos + normals
+           + 12 * F + 12 * V + 16 * F          # face geometry of the BNF setup: read faces + pos, write fc | fa
+           + bnfloop * 48 * F)                 # BNF iterations: f2f + read n + write n + wc*fa
+    return 2 * fwd
+
+
+def loss_phase_roofline(stepper, n_mesh, args, peak, reps=20):
+    """The five losses, forward + backward down to d(loss)/d(pos) and d(loss)/d(norm), captured as one CUDA graph and
+    replayed between CUDA events; L2 is flushed (256 MB memset) before every replay because in the real step the loss
+    kernels run after >10 GB of activation traffic, i.e. on cold index tables."""
+    from dual_dmp_b200._lib import lib
+    from dual_dmp_b200.util import loss as L
+    dev = stepper.device
+    k = args.k
+    pos = stepper.pos.detach().clone().requires_grad_(True)
+    nrm = stepper.norm.detach().clone().requires_grad_(True)
+    tgt_vs, tgt_fn = stepper.tgt_vs, stepper.tgt_fn
+
+    def body():
+        pos.grad = None
+        nrm.grad = None
+        l1 = L.pos_rec_loss(pos, tgt_vs)
+        l2 = L.mesh_laplacian_loss(pos, n_mesh)
+        l3 = L.norm_rec_loss(nrm, tgt_fn)
+        l4, _ = L.fn_bnf_loss(pos, nrm, n_mesh, loop=args.bnfloop)
+        l5 = L.pos_norm_loss(pos, nrm, n_mesh)
+        loss = k[0] * l1 + k[1] * l2 + k[2] * l3 + k[3] * l4 + k[4] * l5
+        loss.backward()
+        return loss.detach()
+
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            body()
+        l0 = lib.query("ddmp_launch_count")
+        body()
+        launches = lib.query("ddmp_launch_count") - l0
+    torch.cuda.current_stream(dev).wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        body()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    ms = []
+    for i in range(reps + 2):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        g.replay()
+        e.record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            ms.append(s.elapsed_time(e))
+    V, F, E = len(n_mesh.vs), len(n_mesh.faces), len(n_mesh.edges)
+    nbytes = loss_bytes(V, F, E, args.bnfloop)
+    t = sum(ms) / len(ms)
+    ach = nbytes / (t * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": "loss phase: pos_rec + laplacian + norm_rec + bnf (setup, %d iteration(s)) + pos_norm, "
+                                      "forward and backward to d/dpos, d/dnorm" % args.bnfloop,
+            "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "frac_of_nominal_8000": ach / 8000.0,
+            "algorithmic_bytes": nbytes, "ms": t, "library_launches": int(launches),
+            "timed_in": "CUDA-graph replay of the loss phase alone, %d replays, L2 flushed before each (cold index "
+                        "tables, as inside the step); the working set (~%d MB) fits L2, so values above the HBM peak "
+                        "would mean cache residency" % (reps, nbytes // 2 // (1 << 20))}
 
 
 class ClockSampler(threading.Thread):
@@ -325,18 +433,9 @@ def run_ours(args):
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
+    loss_roof = loss_phase_roofline(stepper, n_mesh, args, peak)
     achieved = sp_bytes / (sp_ms * 1e-3) / 1e9 if sp_ms > 0 else 0.0
-    # DRAM traffic of the same 48 launches from the committed ncu capture (only meaningful for the benchmark mesh)
-    traffic, traffic_note = None, None
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "spmm_dram_traffic_r1.json")))
-        if args.n == 224 and n_sp:
-            traffic = tj["dram_bytes_per_launch_avg"]
-            traffic_note = ("dram__bytes_read.sum + dram__bytes_write.sum, average per launch over the 48 launches of "
-                            "a step, ncu capture profiles/spmm_dram_r1.csv; algorithmic average per launch = %.0f"
-                            % (sp_bytes / n_sp))
-    except Exception:
-        pass
+    traffic, traffic_note = spmm_traffic(args, n_sp, sp_bytes)
     out = {
         "metric": METRIC, "value": value, "unit": "iters/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -362,7 +461,8 @@ def run_ours(args):
     }
     bf16_sus = float(peaks.get("bf16_tflops_sustained", 1400.0))
     tc_tflops = tc_flop / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
-    out["roofline_tensor"] = {
+    out["roofline"]["by_width_GBps"] = {k_: round(v[1] / (v[0] * 1e-3) / 1e9, 1) for k_, v in by_width.items() if v[0] > 0}
+    out["roofline"]["tensor"] = {
         "bound": "tensor", "kernel": "tc_gemm_nt16x2/nt16 (tcgen05 kind::f16, fp32 emulated with 3 fp16 MMAs: X.W^T and "
                                      "dH.W; tc_gemm_tn16x2/tn16: dH^T.X); all dense transforms of width >= 64",
         "achieved": tc_tflops, "unit": "TFLOP/s", "peak": bf16_sus, "frac": tc_tflops / bf16_sus,
@@ -382,72 +482,173 @@ def run_ours(args):
         "algorithmic_flop_per_step": tc_flop / max(args.steps, 1),
         "ffma_small_width": {"tflops": ff_flop / (ff_ms * 1e-3) / 1e12 if ff_ms > 0 else None,
                              "share_of_step": ff_ms / ms_eager}}
+    out["roofline"]["loss"] = loss_roof
     if args.detail:
         os.makedirs(os.path.dirname(os.path.abspath(args.detail)), exist_ok=True)
         json.dump({k_: {"ms_total": v[0], "GBps": v[1] / (v[0] * 1e-3) / 1e9 if v[0] > 0 else None, "launches": v[2]}
                    for k_, v in by_width.items()}, open(args.detail, "w"), indent=1)
     if not args.no_cpu_baseline and world == 1:
-        out["cpu_baseline"] = cpu_reference(args, steps=2, warmup=1, target_faces=F)
+        torch.cuda.empty_cache()
+        out["cpu_baseline"] = cpu_reference(args, max_steps=1, warmup=1, budget_s=120.0, case=(n_mesh, s_mesh))
     print(json.dumps(out), file=RESULT_OUT, flush=True)
     if dist is not None:
         dist.destroy_process_group()
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-def cpu_reference(args, steps, warmup, target_faces):
-    """The oracle port of the reference's PyG CPU path (oracle/step_ref.py) on a bounded sample, scaled linearly in
-    the face count to the benchmark mesh.  kind="port": torch_geometric is not installable here."""
+ORACLE_BYTES_PER_FACE = 135_000     # resident set of one oracle step (PyG-style saved edge messages), measured: 122-130 KB
+
+
+def _pick_cpu_mesh(args):
+    """the benchmark mesh itself when the host has the RAM for the oracle's saved edge messages, else the largest
+    smaller icosphere that fits (the result is then flagged as extrapolated)"""
+    if args.cpu_n is not None:
+        return args.cpu_n
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 64 << 30
+    for n in (args.n, 160, 128, 100, 64, 40):
+        if n <= args.n and 20 * n * n * ORACLE_BYTES_PER_FACE * 1.15 < avail:
+            return n
+    return 20
+
+
+def _cpu_threads():
+    """thread count for the oracle: quick calibration (one warm + one timed step on a 32,000-face mesh per candidate)"""
     from oracle import step_ref
     from oracle.networks_ref import NormalNetRef, PosNetRef
-    n_mesh, s_mesh, _ = build_case(args.cpu_n)
+    ncpu = os.cpu_count() or 1
+    cands = sorted({min(8, ncpu), min(16, ncpu), ncpu})
+    if len(cands) == 1:
+        return cands[0], {}
+    n_mesh, s_mesh, _ = build_case(40)
+    ds = step_ref.make_dataset(n_mesh, s_mesh)
+    seen = {}
+    for th in cands:
+        torch.set_num_threads(th)
+        torch.manual_seed(0)
+        nets = PosNetRef(), NormalNetRef()
+        opts = [torch.optim.Adam(m.parameters(), lr=0.01) for m in nets]
+        step_ref.train_step(nets[0], nets[1], opts[0], opts[1], ds, n_mesh, epoch=101)
+        t0 = time.perf_counter()
+        step_ref.train_step(nets[0], nets[1], opts[0], opts[1], ds, n_mesh, epoch=102)
+        seen[th] = time.perf_counter() - t0
+    return min(seen, key=seen.get), seen
+
+
+def cpu_reference(args, max_steps, warmup, budget_s, case=None):
+    """The oracle port of the reference's PyG CPU path (oracle/step_ref.py = reference main.py:88-110) timed on the
+    host cores ON THE BENCHMARK MESH: ``warmup`` untimed steps, then whole steps until ``max_steps`` or the time
+    budget is reached.  kind="port": torch_geometric is not installable here.  Nothing is extrapolated unless the
+    host cannot hold the oracle's working set (then the largest mesh that fits is timed and the result is scaled
+    linearly in faces, with ``extrapolated: true``)."""
+    from oracle import step_ref
+    from oracle.networks_ref import NormalNetRef, PosNetRef
+    threads, calib = _cpu_threads()
+    n = _pick_cpu_mesh(args)
+    if case is not None and n == args.n:
+        n_mesh, s_mesh = case
+    else:
+        n_mesh, s_mesh, _ = build_case(n)
     ds = step_ref.make_dataset(n_mesh, s_mesh)
     F = len(n_mesh.faces)
-    best = None
-    for threads in sorted({1, min(8, os.cpu_count() or 1), os.cpu_count() or 1}):
-        torch.set_num_threads(threads)
-        torch.manual_seed(0)
-        posnet, normnet = PosNetRef(), NormalNetRef()
-        opt_pos = torch.optim.Adam(posnet.parameters(), lr=0.01)
-        opt_norm = torch.optim.Adam(normnet.parameters(), lr=0.01)
-        for i in range(warmup):
-            step_ref.train_step(posnet, normnet, opt_pos, opt_norm, ds, n_mesh, tuple(args.k), args.bnfloop, 101 + i)
+    target_faces = 20 * args.n * args.n
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    posnet, normnet = PosNetRef(), NormalNetRef()
+    opt_pos = torch.optim.Adam(posnet.parameters(), lr=0.01)
+    opt_norm = torch.optim.Adam(normnet.parameters(), lr=0.01)
+    t_start = time.perf_counter()
+    for i in range(warmup):
+        step_ref.train_step(posnet, normnet, opt_pos, opt_norm, ds, n_mesh, tuple(args.k), args.bnfloop, 101 + i)
+    times = []
+    while len(times) < max_steps:
         t0 = time.perf_counter()
-        for i in range(steps):
-            step_ref.train_step(posnet, normnet, opt_pos, opt_norm, ds, n_mesh, tuple(args.k), args.bnfloop, 102 + i)
-        dt = (time.perf_counter() - t0) / steps
-        if best is None or dt < best[0]:
-            best = (dt, threads)
-    dt, threads = best
-    return {"value": (1.0 / dt) * (F / float(target_faces)), "unit": "iters/s", "cores": threads, "kind": "port",
-            "sample": f"oracle step on icosphere n={args.cpu_n} ({F} faces): {dt:.3f} s/iter with {threads} threads "
-                      f"(best of 1/8/all), scaled linearly by faces to {target_faces}",
-            "measured_s_per_iter_on_sample": dt, "sample_faces": F}
+        step_ref.train_step(posnet, normnet, opt_pos, opt_norm, ds, n_mesh, tuple(args.k), args.bnfloop,
+                            101 + warmup + len(times))
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_start + times[-1] > budget_s:
+            break
+    dt = sum(times) / len(times)
+    extrapolated = F != target_faces
+    out = {"value": (1.0 / dt) * (F / float(target_faces)), "unit": "iters/s", "cores": threads, "kind": "port",
+           "sample": f"{len(times)} whole step(s) after {warmup} warm-up of the oracle (reference main.py:88-110 restated, "
+                     f"PyG-style GCNConv) on the icosphere n={n} mesh ({F} faces), {threads} threads: {dt:.2f} s/iter"
+                     + ("" if not extrapolated else f"; host RAM too small for {target_faces} faces, scaled linearly"),
+           "extrapolated": extrapolated, "steps_timed": len(times), "warmup_run": warmup,
+           "measured_s_per_iter": dt, "sample_faces": F, "thread_calibration_s_per_iter_at_32000_faces": calib}
+    return out
 
 
 def run_reference(args):
+    """reference arm: rank 0 alone times the CPU oracle on the benchmark mesh; steps / warmup in the line are the ones
+    actually run (a 1M-face oracle step takes tens of seconds, so the time budget, not --steps, ends the loop)"""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from dual_dmp_b200 import synth  # noqa: F401  (host-only generator)
     F_target = 20 * args.n * args.n
-    base = cpu_reference(args, steps=max(1, min(args.steps, 3)), warmup=max(1, min(args.warmup, 1)),
-                         target_faces=F_target)
+    base = cpu_reference(args, max_steps=max(1, args.steps), warmup=1, budget_s=args.cpu_budget_s)
     out = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "iters/s",
-           "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": 1000.0 / base["value"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-           "dtype": "f32", "data": "synthetic",
-           "config": {"workload": f"synthetic icosphere n={args.n}: {F_target} faces, k={args.k}, "
-                                  f"bnfloop={args.bnfloop} (CPU: bounded sample, see cpu_baseline.sample)"},
+           "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": base["steps_timed"], "warmup": base["warmup_run"],
+           "ms_per_step": 1000.0 * base["measured_s_per_iter"], "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": f"synthetic icosphere n={args.n}: {F_target} faces / {10 * args.n * args.n + 2} vertices, "
+                                  f"Gaussian noise 0.2, k={args.k}, bnfloop={args.bnfloop}; CPU oracle timed on "
+                                  f"{base['sample_faces']} faces",
+                      "faces": base["sample_faces"], "requested_steps": args.steps, "requested_warmup": args.warmup,
+                      "extrapolated": base["extrapolated"]},
            "cpu_baseline": base,
            "e2e": {"value": base["value"], "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), file=RESULT_OUT, flush=True)
 
 
-def run_partitioned(args):
-    """mode B: one mesh over all ranks; value = iters/s of that ONE fit (strong scaling)"""
+class PhaseTimer:
+    """CUDA-event brackets around host-side calls (events on the current stream), summed per label"""
+
+    def __init__(self):
+        self.events, self.patches = {}, []
+
+    def patch(self, obj, name, label):
+        fn = getattr(obj, name)
+        timer = self
+
+        def wrapped(*a, **kw):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            out = fn(*a, **kw)
+            e.record()
+            timer.events.setdefault(label, []).append((s, e))
+            return out
+        setattr(obj, name, wrapped)
+        self.patches.append((obj, name, fn))
+
+    def restore(self):
+        for obj, name, fn in reversed(self.patches):
+            setattr(obj, name, fn)
+        self.patches.clear()
+
+    def totals_ms(self):
+        return {k_: sum(s.elapsed_time(e) for s, e in v) for k_, v in self.events.items()}
+
+
+def weak_freq(world, base=224):
+    """icosphere frequency whose face count is closest to world x (20 base^2)"""
+    import math
+    return int(round(base * math.sqrt(world)))
+
+
+def run_partitioned(args, weak):
+    """mode B: ONE mesh range-partitioned over all ranks, per-layer NCCL halo exchange, BatchNorm /
+    gradient all-reduce.  weak: the mesh has world x 1M faces and value is in 1M-face-equivalent iters/s (N = 1 is
+    then exactly the single-GPU benchmark); strong (--mode partition): the --freq mesh, value = iters/s of that fit."""
     import torch.distributed as dist
     from dual_dmp_b200 import dist as D
-    from dual_dmp_b200.partition import PartitionedNet
+    from dual_dmp_b200 import functional as F_
+    from dual_dmp_b200._lib import lib
+    from dual_dmp_b200.partition import PartitionedGraph, PartitionedNet
+    from dual_dmp_b200.step import DualStep
     from dual_dmp_b200.util import loss as L
     from dual_dmp_b200.util.networks import NormalNet, PosNet
     rank, local_rank, world = D.env_rank_world()
@@ -455,67 +656,160 @@ def run_partitioned(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    n_mesh, s_mesh, ds = build_case(args.n)
+    n = weak_freq(world, args.n) if weak else args.n
+    t_setup = time.perf_counter()
+    n_mesh, s_mesh, ds = build_case(n)
     V, F = len(n_mesh.vs), len(n_mesh.faces)
+    F_base = 20 * args.n * args.n
     torch.manual_seed(0)
     posnet, normnet = PosNet(dev).to(dev), NormalNet(dev).to(dev)
     if world > 1:
         ppos, pnrm = PartitionedNet(posnet, rank, world), PartitionedNet(normnet, rank, world)
     else:
         ppos, pnrm = posnet, normnet
-        ds = ds.to(dev)
-    opt_pos = torch.optim.Adam(posnet.parameters(), lr=0.01)
-    opt_norm = torch.optim.Adam(normnet.parameters(), lr=0.01)
-    tgt_vs, tgt_fn = torch.from_numpy(n_mesh.vs).to(dev), torch.from_numpy(n_mesh.fn).to(dev)
-    k = args.k
-
-    def step(epoch):
-        posnet.train(); normnet.train()
-        opt_pos.zero_grad(); opt_norm.zero_grad()
-        pos = ppos(ds)
-        l1 = L.pos_rec_loss(pos, tgt_vs)
-        l2 = L.mesh_laplacian_loss(pos, n_mesh)
-        nrm = pnrm(ds)
-        l3 = L.norm_rec_loss(nrm, tgt_fn)
-        l4, _ = L.fn_bnf_loss(pos, nrm, n_mesh, loop=args.bnfloop)
-        if epoch <= 100:
-            l4 = l4 * 0.0
-        l5 = L.pos_norm_loss(pos, nrm, n_mesh)
-        loss = k[0] * l1 + k[1] * l2 + k[2] * l3 + k[3] * l4 + k[4] * l5
-        loss.backward()
-        torch.nn.utils.clip_grad_norm_(normnet.parameters(), 0.8)
-        opt_pos.step(); opt_norm.step()
-        return loss
-
+    # the reference loop body as one object; eager (no graph capture across NCCL calls), one compute stream
+    stepper = DualStep(ppos, pnrm, ds, n_mesh, k=args.k, bnfloop=args.bnfloop, capture=False, overlap=False)
+    epoch0 = 101
     sampler = ClockSampler(local_rank)
     sampler.start()
-    for i in range(args.warmup):
-        step(101 + i)
-    D.barrier(dev)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        loss = step(101 + args.warmup + i)
-    e1.record()
-    D.barrier(dev)
-    ms = D.max_over_ranks(e0.elapsed_time(e1), dev)
+    for i in range(max(args.warmup, 3)):
+        stepper.step(epoch0 + i)
+    setup_s = time.perf_counter() - t_setup
+
+    def timed(fn, steps):
+        D.barrier(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = lib.query("ddmp_launch_count")
+        e0.record()
+        for i in range(steps):
+            out = fn(i)
+        e1.record()
+        D.barrier(dev)
+        return D.max_over_ranks(e0.elapsed_time(e1), dev), lib.query("ddmp_launch_count") - l0, out
+
+    ms, launches, loss = timed(lambda i: stepper.step(epoch0 + 3 + i), args.steps)
     sampler.stop_flag = True
+    ms_per_step = ms / args.steps
+    scale = (F / float(F_base)) if weak else 1.0
+    value = scale * 1000.0 / ms_per_step
+
+    # ---- per-phase pass: the same steps with event brackets around every communication / kernel group ---------------
+    pt = PhaseTimer()
+    if world > 1:
+        pt.patch(PartitionedGraph, "pack", "halo pack (ddmp_gather_rows)")
+        pt.patch(PartitionedGraph, "all_to_all", "halo all_to_all (NCCL)")
+        pt.patch(PartitionedGraph, "allreduce_", "all_reduce: BatchNorm sums + weight gradients (NCCL)")
+        pt.patch(PartitionedGraph, "gather_outputs", "all_gather of the network outputs")
+    pt.patch(F_, "spmm_gcn", "SpMM")
+    for nm in ("gemm_xw", "gemm_dx", "gemm_dw"):
+        pt.patch(F_, nm, "dense transforms")
+    for nm in ("pos_rec_loss", "mesh_laplacian_loss", "norm_rec_loss", "fn_bnf_loss", "pos_norm_loss"):
+        pt.patch(L, nm, "losses forward (replicated over the whole mesh)")
+    pt.patch(stepper.opt_pos, "step", "clip + Adam")
+    pt.patch(stepper.opt_norm, "step", "clip + Adam")
+    sp_bytes = [0]
+    orig_spmm = F_.spmm_gcn
+
+    def spmm_counted(graph, H, *a, **kw):
+        sp_bytes[0] += spmm_bytes(graph.n, graph.nnz, H.shape[1])
+        return orig_spmm(graph, H, *a, **kw)
+    F_.spmm_gcn = spmm_counted
+    ms_ph, _, _ = timed(lambda i: stepper.step(epoch0 + 3 + args.steps + i), args.steps)
+    F_.spmm_gcn = orig_spmm
+    pt.restore()
+    torch.cuda.synchronize()
+    phases = {k_: v / args.steps for k_, v in pt.totals_ms().items()}
+    phases["whole step (this pass)"] = ms_ph / args.steps
+    sp_ms = pt.totals_ms().get("SpMM", 0.0)
+
+    # ---- e2e: this rank's slice of the inputs + the (replicated) float64 targets from pinned host memory every step,
+    #      loss read back
+    e2e = None
+    if not args.no_e2e:
+        if world > 1:
+            pg_p, pg_n = posnet.last_graph, normnet.last_graph
+            ids_p, ids_n = pg_p.own_ids.cpu(), pg_n.own_ids.cpu()
+            host = {"z1": ds.z1.detach()[ids_p].contiguous().pin_memory(),
+                    "x_pos": ds.x_pos.detach()[ids_p].contiguous().pin_memory(),
+                    "z2": ds.z2.detach()[ids_n].contiguous().pin_memory()}
+            dst = {"z1": ppos._cache[3], "x_pos": ppos._cache[4], "z2": pnrm._cache[3]}
+        else:
+            host = {"z1": ds.z1.detach().pin_memory(), "x_pos": ds.x_pos.detach().pin_memory(),
+                    "z2": ds.z2.detach().pin_memory()}
+            dst = {"z1": stepper.dataset.z1, "x_pos": stepper.dataset.x_pos, "z2": stepper.dataset.z2}
+        host["tgt_vs"] = torch.from_numpy(n_mesh.vs).pin_memory()
+        host["tgt_fn"] = torch.from_numpy(n_mesh.fn).pin_memory()
+        dst["tgt_vs"], dst["tgt_fn"] = stepper.tgt_vs, stepper.tgt_fn
+        h2d = sum(t.numel() * t.element_size() for t in host.values())
+
+        def e2e_step(i):
+            with torch.no_grad():
+                for k_, t in host.items():
+                    dst[k_].copy_(t, non_blocking=True)
+            return stepper.step(epoch0 + 3 + 2 * args.steps + i).item()
+
+        e2e_step(0)
+        ms_e, _, _ = timed(e2e_step, args.steps)
+        e2e = {"value": scale * 1000.0 * args.steps / ms_e, "unit": "iters/s", "h2d_bytes_per_step": int(h2d) * world,
+               "d2h_bytes_per_step": 8 * world,
+               "path": "every step: each rank uploads its slice of z1/z2/x_pos and the float64 targets from pinned host "
+                       "memory, runs DualStep.step over the PartitionedNets, reads the loss back (.item())"}
+
     halo = {}
     if world > 1:
         for name, net in (("vertex_graph", posnet), ("face_graph", normnet)):
             g = net.last_graph
             halo[name] = {"owned_rows": g.n, "halo_rows": g.n_halo, "sent_rows": g.n_send}
     mem = torch.cuda.max_memory_allocated(dev) / 2 ** 30
+
+    # ---- side measurement: mode A (one independent 1M-face fit per GPU, no data-path collective) ---------------------
+    mode_a = None
+    if weak and world > 1 and not args.no_mode_a:
+        del stepper, ppos, pnrm
+        torch.cuda.empty_cache()
+        n_mesh1, s_mesh1, ds1 = build_case(args.n)
+        torch.manual_seed(0)
+        p1, q1 = PosNet(dev).to(dev), NormalNet(dev).to(dev)
+        st1 = DualStep(p1, q1, ds1, n_mesh1, k=args.k, bnfloop=args.bnfloop)
+        for i in range(5):
+            st1.step(epoch0 + i)
+        ms_a, _, _ = timed(lambda i: st1.step(epoch0 + 5 + i), args.steps)
+        mode_a = {"value": world * 1000.0 * args.steps / ms_a, "unit": "iters/s", "ms_per_step": ms_a / args.steps,
+                  "what": "one independent 1M-face fit per GPU (BASELINE configs[3] mechanism), CUDA-graph DualStep, no "
+                          "data-path collective"}
+
     if rank == 0:
-        out = {"metric": METRIC, "value": 1000.0 * args.steps / ms, "unit": "iters/s", "n_gpus": world,
-               "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-               "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-               "config": {"workload": f"ONE synthetic icosphere n={args.n}: {F} faces / {V} vertices, Morton "
-                                      f"range-partitioned over {world} GPU(s), per-layer NCCL halo exchange, "
-                                      f"BatchNorm-statistic and weight-gradient all-reduce, replicated losses",
-                          "faces": F, "vertices": V, "mode": "partition", "rank0_partition": halo,
-                          "rank0_peak_mem_GiB": round(mem, 2)},
-               "e2e": None, "loss": float(loss.detach()), "clocks": sampler.summary()}
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        ach = sp_bytes[0] / (sp_ms * 1e-3) / 1e9 if sp_ms > 0 else 0.0
+        limiter = max(((k_, v) for k_, v in phases.items() if "NCCL" in k_ or "all_gather" in k_ or "pack" in k_
+                       or "losses" in k_), key=lambda kv: kv[1], default=(None, 0.0))
+        out = {"metric": METRIC, "value": value, "unit": "iters/s", "n_gpus": world, "steps": args.steps,
+               "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+               "scaling": "weak" if weak else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+               "config": {"workload": (f"ONE synthetic icosphere n={n}: {F} faces / {V} vertices = {world} x ~1M faces, "
+                                       f"Morton range-partitioned over {world} GPU(s), per-layer NCCL halo exchange, "
+                                       f"BatchNorm-statistic and weight-gradient all-reduce, replicated losses; value = "
+                                       f"(faces / {F_base}) x iters/s (1M-face-equivalent iterations per second)")
+                          if weak else
+                          (f"ONE synthetic icosphere n={n}: {F} faces / {V} vertices, Morton range-partitioned over "
+                           f"{world} GPU(s) (strong scaling), per-layer NCCL halo exchange"),
+                          "faces": F, "vertices": V, "mode": "partition-weak" if weak else "partition",
+                          "iters_per_s_of_this_mesh": 1000.0 / ms_per_step, "rank0_partition": halo,
+                          "rank0_peak_mem_GiB": round(mem, 2), "setup_s": round(setup_s, 1),
+                          "l2_policy": "working set (>=10 GB of saved activations per rank) exceeds L2",
+                          "phases_ms_per_step_rank0": {k_: round(v, 3) for k_, v in sorted(phases.items())},
+                          "largest_non_compute_phase": limiter[0],
+                          "mode_a_replicas": mode_a},
+               "e2e": e2e, "gpu_launches": int(launches), "loss": float(loss.detach()),
+               "roofline": {"bound": "hbm", "kernel": "spmm_gcn_kernel (rank 0's aggregation launches over its owned rows)",
+                            "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak if peak else None,
+                            "traffic": None, "timed_in": "per-phase pass (event brackets, same steps)"},
+               "clocks": sampler.summary()}
         print(json.dumps(out), file=RESULT_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -523,9 +817,12 @@ def run_partitioned(args):
 
 if __name__ == "__main__":
     a = parse_args()
+    world_ = int(os.environ.get("WORLD_SIZE", "1"))
     if a.impl == "reference":
         run_reference(a)
     elif a.mode == "partition":
-        run_partitioned(a)
+        run_partitioned(a, weak=False)
+    elif a.mode == "partition-weak" or (a.mode == "auto" and world_ > 1):
+        run_partitioned(a, weak=True)
     else:
         run_ours(a)

@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "../../include/ddmp_b200.h"
 
 namespace ddmp {
@@ -82,6 +84,20 @@ __device__ __forceinline__ bool publish_and_am_last(unsigned int* ticket, unsign
     if (is_last) __threadfence();
     return is_last;
 }
+
+// "Done once per device" flag for per-device function attributes (cudaFuncSetAttribute is per device/context, the
+// library can be driven on several devices of one process through ddmp_set_device, and launchers are called from the
+// main thread and from the autograd thread): one bit per device ordinal, set with an atomic OR.
+struct PerDeviceOnce {
+    std::atomic<unsigned long long> done{0ull};
+    static unsigned long long bit() {
+        int d = 0;
+        cudaGetDevice(&d);
+        return 1ull << (d & 63);
+    }
+    bool need() const { return (done.load(std::memory_order_acquire) & bit()) == 0ull; }
+    void mark() { done.fetch_or(bit(), std::memory_order_release); }
+};
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }

@@ -301,11 +301,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_nt_kernel(const NtArgs g)
 template <int BN, int STAGES>
 static int launch_nt(const NtArgs& g, cudaStream_t st) {
     constexpr size_t smem = (size_t)STAGES * (2 * BM * 128 + 2 * BN * 128) + 1024 + 256;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (configured.need()) {
         DDMP_CUDA(cudaFuncSetAttribute(tc_gemm_nt_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
-        configured = true;
+        configured.mark();
     }
     const int64_t tiles = ceil_div(g.M, BM) * g.tiles_n;
     DDMP_REQUIRE(tiles < (1ll << 31), "tc gemm: too many tiles");
@@ -653,11 +653,11 @@ __global__ void __launch_bounds__(kV2Threads, 1) tc_gemm_nt2_kernel(const Nt2Arg
 template <int BN, int STAGES, bool DEEP, int KB>
 static int launch_nt2_impl(const Nt2Args& g, cudaStream_t st) {
     constexpr size_t smem = (size_t)STAGES * (2 * BM * KB * 4 + 2 * BN * KB * 4) + 1024 + 256 + 4 * 32 * 128;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (configured.need()) {
         DDMP_CUDA(cudaFuncSetAttribute(tc_gemm_nt2_kernel<BN, STAGES, DEEP, KB>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+        configured.mark();
     }
     const int64_t grid = g.num_tiles < kNumSMs ? g.num_tiles : kNumSMs;
     tc_gemm_nt2_kernel<BN, STAGES, DEEP, KB><<<(unsigned)grid, kV2Threads, smem, st>>>(g);
@@ -982,10 +982,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kV2Threads, 1) tc_ge
 
 static int launch_nt3(const Nt2Args& g0, cudaStream_t st) {
     constexpr size_t smem = (size_t)kNt3Stages * (2 * BM * 128 + 2 * (kNt3BN / 2) * 128) + 1024 + 256 + 4 * 32 * 128;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (configured.need()) {
         DDMP_CUDA(cudaFuncSetAttribute(tc_gemm_nt3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+        configured.mark();
     }
     Nt2Args g = g0;
     g.num_tiles = ceil_div(g.M, 2 * BM) * g.tiles_n;     // pair tiles of 256 rows
@@ -1476,11 +1476,11 @@ __global__ void __launch_bounds__(kV2Threads, 1) tc_gemm_nt16_kernel(const Nt16A
 template <int BN, int STAGES>
 static int launch_nt16(const Nt16Args& g, cudaStream_t st) {
     constexpr size_t smem = (size_t)STAGES * (2 * BM * 128 + 2 * BN * 128) + 1024 + 256 + 4 * 32 * 128;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (configured.need()) {
         DDMP_CUDA(cudaFuncSetAttribute(tc_gemm_nt16_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
-        configured = true;
+        configured.mark();
     }
     const int64_t grid = g.num_tiles < kNumSMs ? g.num_tiles : kNumSMs;
     tc_gemm_nt16_kernel<BN, STAGES><<<(unsigned)grid, kV2Threads, smem, st>>>(g);
@@ -1671,10 +1671,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kV2Threads, 1) tc_ge
 
 static int launch_nt16x2(const Nt16Args& g0, cudaStream_t st) {
     constexpr size_t smem = (size_t)kNt16x2Stages * (2 * BM * 128 + 2 * 128 * 128) + 1024 + 256 + 4 * 32 * 128;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (configured.need()) {
         DDMP_CUDA(cudaFuncSetAttribute(tc_gemm_nt16x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+        configured.mark();
     }
     Nt16Args g = g0;
     g.num_tiles = ceil_div(g.M, 2 * BM) * g.tiles_n;
@@ -1947,11 +1947,11 @@ __global__ void seg_reduce_kernel(const float* __restrict__ partials, float* __r
 template <int BN, int STAGES, int PW>
 static int launch_tn_impl(const TnArgs& g, cudaStream_t st) {
     constexpr size_t smem = (size_t)STAGES * (2 * BM * 128 + 2 * BN * 128) + 1024 + 256;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (configured.need()) {
         DDMP_CUDA(cudaFuncSetAttribute(tc_gemm_tn_kernel<BN, STAGES, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
-        configured = true;
+        configured.mark();
     }
     const int64_t grid = g.num_items < kNumSMs ? g.num_items : kNumSMs;
     tc_gemm_tn_kernel<BN, STAGES, PW><<<(unsigned)grid, PW * 32 + 32, smem, st>>>(g);
@@ -2190,11 +2190,11 @@ __global__ void __launch_bounds__(16 * 32 + 32, 1) tc_gemm_tn16_kernel(const Tn1
 template <int BN, int STAGES>
 static int launch_tn16(const Tn16Args& g, cudaStream_t st) {
     constexpr size_t smem = (size_t)STAGES * (2 * BM * BK16 * 2 + 2 * BN * BK16 * 2) + 1024 + 256;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (configured.need()) {
         DDMP_CUDA(cudaFuncSetAttribute(tc_gemm_tn16_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
-        configured = true;
+        configured.mark();
     }
     const int64_t grid = g.num_items < kNumSMs ? g.num_items : kNumSMs;
     tc_gemm_tn16_kernel<BN, STAGES><<<(unsigned)grid, 16 * 32 + 32, smem, st>>>(g);
@@ -2433,11 +2433,11 @@ template <int NACC>
 static int launch_tn16x2(const Tn16Args& g, cudaStream_t st) {
     constexpr int STAGES = (NACC == 2) ? 2 : 3;
     constexpr size_t smem = (size_t)STAGES * (2 * BM * BK16 * 2 + NACC * 2 * 128 * BK16 * 2) + 1024 + 256;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (configured.need()) {
         DDMP_CUDA(cudaFuncSetAttribute(tc_gemm_tn16x2_kernel<NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
-        configured = true;
+        configured.mark();
     }
     const int64_t pairs = g.num_items < kNumSMs / 2 ? g.num_items : kNumSMs / 2;
     tc_gemm_tn16x2_kernel<NACC><<<(unsigned)(2 * pairs), 16 * 32 + 32, smem, st>>>(g);

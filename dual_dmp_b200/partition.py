@@ -116,21 +116,37 @@ class PartitionedGraph:
         # caller numbering of the rows this rank owns (for slicing inputs / assembling outputs)
         self.own_ids = torch.from_numpy(plan.perm[self.lo:self.hi].copy()).to(dev)
         self.perm_all = torch.from_numpy(plan.perm.copy()).to(dev)
+        self._send_bufs: dict = {}                           # width -> persistent packed-rows buffer
 
     # ---- collectives (NCCL on GPUs; enqueued on the current stream, no host synchronisation) -----------------------
     def exchange(self, X_ext: torch.Tensor) -> None:
         """fill the halo rows X_ext[n_own:] with the owners' current rows of X_ext[:n_own] (all ranks call this)"""
+        self.all_to_all(X_ext, self.pack(X_ext))
+
+    def pack(self, X_ext: torch.Tensor) -> torch.Tensor:
+        """boundary rows every peer needs, grouped by destination rank, in a persistent buffer per width"""
         C = X_ext.shape[1]
-        send = torch.empty(self.n_send, C, dtype=torch.float32, device=self.device)
+        send = self._send_bufs.get(C)
+        if send is None:
+            send = self._send_bufs[C] = torch.empty(self.n_send, C, dtype=torch.float32, device=self.device)
         if self.n_send:
             lib.call("ddmp_gather_rows", ptr(X_ext), ptr(self.send_idx), ptr(send), self.n_send, C,
                      stream_ptr(self.device))
+        return send
+
+    def all_to_all(self, X_ext: torch.Tensor, send: torch.Tensor) -> None:
         dist.all_to_all_single(X_ext[self.n:], send, output_split_sizes=self.recv_counts,
                                input_split_sizes=self.send_counts, group=self.group)
 
     def allreduce_(self, t: torch.Tensor) -> torch.Tensor:
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
         return t
+
+    def all_gather_equal(self, mine: torch.Tensor) -> List[torch.Tensor]:
+        """rank-ordered list of every rank's (equally shaped) tensor"""
+        parts = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(parts, mine, group=self.group)
+        return parts
 
     def gather_outputs(self, out_own: torch.Tensor) -> torch.Tensor:
         """[n_own, k] rows of every rank -> [N, k] in the CALLER's numbering (same on all ranks)"""
@@ -145,8 +161,7 @@ class _AllGatherRows(torch.autograd.Function):
         m = max(sizes)                                        # ranges differ by at most one row: pad to equal size
         mine = torch.zeros(m, k, dtype=out_own.dtype, device=out_own.device)
         mine[: out_own.shape[0]] = out_own
-        parts = [torch.empty(m, k, dtype=out_own.dtype, device=out_own.device) for _ in sizes]
-        dist.all_gather(parts, mine, group=pg.group)
+        parts = pg.all_gather_equal(mine)
         full_sorted = torch.cat([p[:s] for p, s in zip(parts, sizes)], dim=0)     # Morton order
         full = torch.empty_like(full_sorted)
         full[pg.perm_all] = full_sorted                      # caller's numbering
@@ -172,6 +187,10 @@ class PartitionedNet(torch.nn.Module):
         super().__init__()
         self.net, self.rank, self.world, self.group = net, int(rank), int(world), group
         self._cache = None
+
+    @property
+    def device(self):
+        return self.net.device
 
     def _prepare(self, data):
         from . import functional as F_
