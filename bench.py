@@ -144,12 +144,15 @@ def loss_phase_roofline(stepper, n_mesh, args, peak, reps=20):
     def body():
         pos.grad = None
         nrm.grad = None
-        l1 = L.pos_rec_loss(pos, tgt_vs)
-        l2 = L.mesh_laplacian_loss(pos, n_mesh)
-        l3 = L.norm_rec_loss(nrm, tgt_fn)
-        l4, _ = L.fn_bnf_loss(pos, nrm, n_mesh, loop=args.bnfloop)
-        l5 = L.pos_norm_loss(pos, nrm, n_mesh)
-        loss = k[0] * l1 + k[1] * l2 + k[2] * l3 + k[3] * l4 + k[4] * l5
+        if stepper.fused_loss:          # what DualStep runs: one cooperative kernel (ddmp_dual_loss) + two scalings
+            loss, _ = L.dual_loss(pos, nrm, n_mesh, tgt_vs, tgt_fn, k, args.bnfloop, 1.0)
+        else:
+            l1 = L.pos_rec_loss(pos, tgt_vs)
+            l2 = L.mesh_laplacian_loss(pos, n_mesh)
+            l3 = L.norm_rec_loss(nrm, tgt_fn)
+            l4, _ = L.fn_bnf_loss(pos, nrm, n_mesh, loop=args.bnfloop)
+            l5 = L.pos_norm_loss(pos, nrm, n_mesh)
+            loss = k[0] * l1 + k[1] * l2 + k[2] * l3 + k[3] * l4 + k[4] * l5
         loss.backward()
         return loss.detach()
 
@@ -181,8 +184,9 @@ def loss_phase_roofline(stepper, n_mesh, args, peak, reps=20):
     nbytes = loss_bytes(V, F, E, args.bnfloop)
     t = sum(ms) / len(ms)
     ach = nbytes / (t * 1e-3) / 1e9
-    return {"bound": "hbm", "kernel": "loss phase: pos_rec + laplacian + norm_rec + bnf (setup, %d iteration(s)) + pos_norm, "
-                                      "forward and backward to d/dpos, d/dnorm" % args.bnfloop,
+    return {"bound": "hbm", "kernel": ("dual_loss_kernel (one cooperative launch): " if stepper.fused_loss else "loss phase: ")
+                                      + "pos_rec + laplacian + norm_rec + bnf (setup, %d iteration(s)) + pos_norm, "
+                                        "forward and backward to d/dpos, d/dnorm" % args.bnfloop,
             "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "frac_of_nominal_8000": ach / 8000.0,
             "algorithmic_bytes": nbytes, "ms": t, "library_launches": int(launches),
             "timed_in": "CUDA-graph replay of the loss phase alone, %d replays, L2 flushed before each (cold index "
@@ -348,6 +352,13 @@ def run_ours(args):
     F_.spmm_gcn = spmm_timed
     F_.gemm_xw, F_.gemm_dx, F_.gemm_dw = (timed_gemm(orig_gemms[0], "xw"), timed_gemm(orig_gemms[1], "dx"),
                                           timed_gemm(orig_gemms[2], "dw"))
+    pt = PhaseTimer()
+    pt.patch(F_, "bn_bwd_spmm_tile", "BatchNorm backward + backward aggregation (reduce, finalize, fused tile kernel)")
+    pt.patch(F_, "bn_lrelu_backward", "BatchNorm backward (reduce, finalize, apply)")
+    pt.patch(F_, "bn_stats_finalize", "BatchNorm statistics finalize")
+    pt.patch(L, "dual_loss", "losses forward+backward (dual_loss_kernel)")
+    pt.patch(stepper.opt_pos, "step", "clip + Adam")
+    pt.patch(stepper.opt_norm, "step", "clip + Adam")
     was_overlap, stepper.overlap = stepper.overlap, False      # one stream: per-launch events must not time-slice
     # Per-launch events are only meaningful while the GPU, not the host, is the bottleneck: an event pair around a
     # launch also covers the time the GPU waits for that launch to arrive.  Two untimed eager steps absorb one-time
@@ -374,7 +385,9 @@ def run_ours(args):
     stepper.overlap = was_overlap
     F_.spmm_gcn = orig_spmm
     F_.gemm_xw, F_.gemm_dx, F_.gemm_dw = orig_gemms
+    pt.restore()
     torch.cuda.synchronize()
+    phases = {k_: v / args.steps for k_, v in pt.totals_ms().items()}
     tc_ms = sum(s.elapsed_time(e) for s, e, _, tc, _ in gemm_events if tc)
     tc_flop = sum(f for _, _, f, tc, _ in gemm_events if tc)
     tc16_ms = sum(s.elapsed_time(e) for s, e, _, tc, f16 in gemm_events if tc and f16)
@@ -483,6 +496,11 @@ def run_ours(args):
         "ffma_small_width": {"tflops": ff_flop / (ff_ms * 1e-3) / 1e12 if ff_ms > 0 else None,
                              "share_of_step": ff_ms / ms_eager}}
     out["roofline"]["loss"] = loss_roof
+    phases["GCN aggregation, forward (+ backward when unfused)"] = sp_ms / args.steps
+    phases["dense transforms, tensor cores"] = tc_ms / args.steps
+    phases["dense transforms, FFMA (width < 64)"] = ff_ms / args.steps
+    phases["whole eager step"] = ms_eager / args.steps
+    out["config"]["phases_ms_per_step"] = {k_: round(v, 3) for k_, v in sorted(phases.items())}
     if args.detail:
         os.makedirs(os.path.dirname(os.path.abspath(args.detail)), exist_ok=True)
         json.dump({k_: {"ms_total": v[0], "GBps": v[1] / (v[0] * 1e-3) / 1e9 if v[0] > 0 else None, "launches": v[2]}

@@ -14,7 +14,8 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libddmp_b200.so")
+# DDMP_LIB_PATH: load another build of the SAME library (kernel A/B experiments: scripts/build_variant.sh); never a fallback
+LIB_PATH = os.environ.get("DDMP_LIB_PATH") or os.path.join(_HERE, "lib", "libddmp_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "ddmp_b200.h")
 
 _CTYPES = {

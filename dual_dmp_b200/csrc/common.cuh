@@ -99,6 +99,17 @@ struct PerDeviceOnce {
     void mark() { done.fetch_or(bit(), std::memory_order_release); }
 };
 
+// tile-staged aggregation kernel (spmm_tile.cu)
+bool spmm_tile_supported(int64_t n, int C);
+int spmm_tile_set(int on);
+int spmm_bn_bwd_tile_rows(int C);
+int spmm_bn_bwd_tile_launch(const int* rowptr, const int* col, const float* w, const float* gX, const float* Y,
+                            const float* mean, const float* rstd, const float* scale, const float* shift,
+                            const float* c1, const float* c2, float slope, float* dH, float* colsum, float* amax,
+                            int64_t n, int C, cudaStream_t st);
+int spmm_tile_launch(const int* rowptr, const int* col, const float* w, const float* H, const float* bias, float* Y,
+                     float* partials, float* amax, int64_t n, int C, cudaStream_t st);
+
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 

@@ -1744,7 +1744,10 @@ static int run_nt16(const float* A, const int* a_map, const float* scale, const 
 // tile; a fixed-order float64 reduction sums the segments (deterministic, and it bounds the fp32 accumulation
 // length inside TMEM to kSegRows: the tensor core truncates when it accumulates, so the error grows linearly
 // with the chain length, measured ~7e-9 per row).
-constexpr int kSegRows = 2048;
+#ifndef DDMP_SEG_ROWS
+#define DDMP_SEG_ROWS 2048
+#endif
+constexpr int kSegRows = DDMP_SEG_ROWS;
 
 struct TnArgs {
     const float* A;       // dH [rows, M] row-major

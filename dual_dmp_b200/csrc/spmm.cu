@@ -392,6 +392,7 @@ int ddmp_spmm_gcn(const int32_t* rowptr, const int32_t* col, const float* w, con
     if (n == 0) return DDMP_OK;
     DDMP_REQUIRE(rowptr && col && w && H && Y, "spmm_gcn: null pointer");
     cudaStream_t st = as_stream(stream);
+    if (spmm_tile_supported(n, C)) return spmm_tile_launch(rowptr, col, w, H, bias, Y, stats_partials, amax_blocks, n, C, st);
     switch (C) {
         case 32: return launch_spmm<32>(rowptr, col, w, H, bias, Y, stats_partials, amax_blocks, n, st);
         case 64: return launch_spmm<64>(rowptr, col, w, H, bias, Y, stats_partials, amax_blocks, n, st);
@@ -406,6 +407,37 @@ int ddmp_spmm_gcn(const int32_t* rowptr, const int32_t* col, const float* w, con
     }
     spmm_gcn_generic_kernel<<<(unsigned)ceil_div(n, 8), 256, 0, st>>>(rowptr, col, w, H, bias, Y, n, C);
     return check_launch("spmm_gcn_generic");
+}
+
+int64_t ddmp_spmm_bn_bwd_tile_blocks(int64_t n, int32_t C) {
+    const int r = ddmp::spmm_bn_bwd_tile_rows(C);
+    return n <= 0 ? 0 : (n + r - 1) / r;
+}
+
+int64_t ddmp_spmm_bn_bwd_tile_amax_len(int64_t n, int32_t C) {
+    return ddmp_spmm_bn_bwd_tile_blocks(n, C) * (C > 128 ? C / 128 : 1);
+}
+
+int ddmp_spmm_bn_bwd_tile(const int32_t* rowptr, const int32_t* col, const float* w, const float* gX, const float* Y,
+                          const float* mean, const float* rstd, const float* scale, const float* shift,
+                          const float* c1, const float* c2, float slope, float* dH, float* colsum_partials,
+                          float* amax_blocks, int64_t n, int32_t C, void* stream) {
+    using namespace ddmp;
+    DDMP_REQUIRE(n >= 0 && n < (1ll << 31), "spmm_bn_bwd_tile: bad row count");
+    DDMP_REQUIRE(C == 32 || C == 64 || (C >= 128 && C <= 512 && C % 128 == 0),
+                 "spmm_bn_bwd_tile: C must be 32, 64 or a multiple of 128 up to 512 (got %d)", C);
+    if (n == 0) return DDMP_OK;
+    DDMP_REQUIRE(rowptr && col && w && gX && Y && mean && rstd && scale && shift && c1 && c2 && dH,
+                 "spmm_bn_bwd_tile: null pointer");
+    return spmm_bn_bwd_tile_launch(rowptr, col, w, gX, Y, mean, rstd, scale, shift, c1, c2, slope, dH, colsum_partials,
+                                   amax_blocks, n, C, as_stream(stream));
+}
+
+int ddmp_spmm_use_tile_kernel(int mode) { return ddmp::spmm_tile_set(mode); }
+
+int64_t ddmp_spmm_amax_len(int64_t n, int32_t C) {
+    const int64_t nblk = ddmp_num_row_blocks(n, C);
+    return ddmp::spmm_tile_supported(n, C) && C > 128 ? nblk * (C / 128) : nblk;
 }
 
 int ddmp_spmm_bn_bwd(const int32_t* rowptr, const int32_t* col, const float* w, const float* gX, const float* Y,

@@ -7,6 +7,8 @@ activated tensors are recomputed on load by the consumers (SURVEY.md §7 hard pa
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from ._lib import lib, ptr, require_cuda, set_device, stream_ptr
@@ -20,6 +22,11 @@ GEMM_BACKEND = 0    # DDMP_GEMM_AUTO; tests may set 1 (FFMA) / 2 (tcgen05)
 # on B200 at 1M faces the doubled gather volume through L2 costs more than the two saved passes over dY (C=512:
 # 1.82 vs 1.37 ms vertex graph, 2.87 vs 2.52 ms face graph; scripts/bench_bn_spmm.py) -- kept for narrower graphs.
 FUSE_BN_SPMM = False
+# backward: BatchNorm/LeakyReLU "apply" folded into the TILE-staged aggregation kernel (ddmp_spmm_bn_bwd_tile): dY of a row
+# block is formed once in shared memory from the TMA-staged gX / Y tiles, so the gather volume does not double and dY
+# never goes to HBM (3 tensor passes per layer instead of 5).  Single-GPU path only (the partitioned mode exchanges dY).
+FUSE_BN_SPMM_TILE = os.environ.get("DDMP_FUSE_BN_TILE", "1") != "0"
+TILE_WIDTHS = (32, 64, 128, 256, 384, 512)
 
 HEAD_POS, HEAD_NORM = 0, 1
 
@@ -47,7 +54,7 @@ def spmm_gcn(graph: GcnGraph, H, bias=None, stats=False, transposed=False, out=N
     rowptr, col, w = (graph.rowptr_t, graph.col_t, graph.w_t) if transposed else (graph.rowptr, graph.col, graph.w)
     Y = out if out is not None else torch.empty(n, C, dtype=torch.float32, device=H.device)
     partials = torch.empty(num_row_blocks(n, C), 2, C, dtype=torch.float32, device=H.device) if stats else None
-    ab = torch.empty(num_row_blocks(n, C), dtype=torch.float32, device=H.device) if amax else None
+    ab = torch.empty(int(lib.query("ddmp_spmm_amax_len", n, C)), dtype=torch.float32, device=H.device) if amax else None
     lib.call("ddmp_spmm_gcn", ptr(rowptr), ptr(col), ptr(w), ptr(H), ptr(bias), ptr(Y), ptr(partials), ptr(ab), n, C,
              stream_ptr(H.device))
     if amax:
@@ -180,6 +187,33 @@ def bn_bwd_spmm_fused(graph, gX, Y, stats, dH_out=None):
     return dH, small[0], small[1], small[4]
 
 
+def bn_bwd_spmm_tile(graph, gX, Y, stats, dH_out=None, amax=False):
+    """BatchNorm/LeakyReLU backward + backward aggregation on the tile-staged kernel: reduce (sum gZ, sum gZ*xhat) ->
+    finalize -> ddmp_spmm_bn_bwd_tile (dY formed in shared memory, never written).  Returns
+    (dH, dgamma, dbeta, dbias, amax_blocks or None)."""
+    n, C = Y.shape
+    dev = Y.device
+    st = stream_ptr(dev)
+    nblk = num_row_blocks(n, C)
+    partials = torch.empty(nblk, 2, C, dtype=torch.float32, device=dev)
+    small = torch.empty(5, C, dtype=torch.float32, device=dev)             # dgamma, dbeta, c1, c2, dbias
+    mean, rstd, scale, shift = stats[0], stats[1], stats[2], stats[3]
+    lib.call("ddmp_bn_bwd_reduce", ptr(gX), ptr(Y), ptr(mean), ptr(rstd), ptr(scale), ptr(shift), SLOPE,
+             ptr(partials), n, C, st)
+    lib.call("ddmp_bn_bwd_finalize", ptr(partials), nblk, n, C, ptr(small[0]), ptr(small[1]), ptr(small[2]),
+             ptr(small[3]), st)
+    dH = dH_out if dH_out is not None else torch.empty_like(Y)
+    nblk_t = int(lib.query("ddmp_spmm_bn_bwd_tile_blocks", n, C))
+    colsum = torch.empty(nblk_t, 1, C, dtype=torch.float32, device=dev)
+    ab = torch.empty(int(lib.query("ddmp_spmm_bn_bwd_tile_amax_len", n, C)), dtype=torch.float32, device=dev) \
+        if amax else None
+    lib.call("ddmp_spmm_bn_bwd_tile", ptr(graph.rowptr), ptr(graph.col), ptr(graph.w), ptr(gX), ptr(Y), ptr(mean),
+             ptr(rstd), ptr(scale), ptr(shift), ptr(small[2]), ptr(small[3]), SLOPE, ptr(dH), ptr(colsum), ptr(ab), n, C,
+             st)
+    lib.call("ddmp_colsum_finalize", ptr(colsum), nblk_t, 1, C, ptr(small[4]), st)
+    return dH, small[0], small[1], small[4], ab
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # operator-level GCNConv  (drop-in for torch_geometric.nn.GCNConv.forward, reference util/networks.py:15-26)
 # ---------------------------------------------------------------------------------------------------------------------
@@ -300,7 +334,7 @@ class GcnNetFunction(torch.autograd.Function):
         comm = graph if hasattr(graph, "exchange") else None
         n_ext = graph.n_ext if comm is not None else n
         bufA = torch.empty(n * cmax, dtype=torch.float32, device=dev)      # gX (grad wrt activated layer output)
-        fused = comm is None and FUSE_BN_SPMM and graph.symmetric
+        fused = comm is None and (FUSE_BN_SPMM or FUSE_BN_SPMM_TILE) and graph.symmetric
         bufB = None if fused else torch.empty(n_ext * cmax, dtype=torch.float32, device=dev)   # dY ([owned | halo])
         bufC = torch.empty(n * cmax, dtype=torch.float32, device=dev)      # dH
         gX = bufA[: n * 32].view(n, 32)
@@ -317,9 +351,14 @@ class GcnNetFunction(torch.autograd.Function):
             cout, cin = Ws[l].shape
             dH = bufC[: n * cout].view(n, cout)
             dh_max = None                           # row-block maxima of |dH| when the aggregation kernel provides them
-            if comm is None and FUSE_BN_SPMM and graph.symmetric and cout in (32, 64, 128, 256, 512):
+            if comm is None and FUSE_BN_SPMM_TILE and graph.symmetric and cout in TILE_WIDTHS:
+                _, dgamma, dbeta, dbias, dh_max = bn_bwd_spmm_tile(graph, gX, Ys[l], stats[l], dH_out=dH,
+                                                                   amax=cout in AMAX_WIDTHS and l > 0)
+            elif comm is None and FUSE_BN_SPMM and graph.symmetric and cout in (32, 64, 128, 256, 512):
                 _, dgamma, dbeta, dbias = bn_bwd_spmm_fused(graph, gX, Ys[l], stats[l], dH_out=dH)
             else:
+                if bufB is None:
+                    bufB = torch.empty(n_ext * cmax, dtype=torch.float32, device=dev)
                 dY = bufB[: n_ext * cout].view(n_ext, cout)
                 _, dgamma, dbeta, dbias = bn_lrelu_backward(gX, Ys[l], stats[l], dY_out=dY, comm=comm)
                 if comm is not None:
@@ -500,6 +539,41 @@ class BnfLoss(torch.autograd.Function):
             g = g_in
         ctx.normals = None
         return None, g, None, None
+
+
+class DualLoss(torch.autograd.Function):
+    """The loss phase of one iteration (reference main.py:94-106) as one cooperative kernel: returns the weighted total
+    (float64) and the five terms; the gradients w.r.t. ``pos`` / ``norm`` are produced by the same launch and only
+    scaled by the upstream gradient in ``backward``."""
+
+    @staticmethod
+    def forward(ctx, pos, nrm, tgt_vs, tgt_fn, topo, k, loop, bnf_scale):
+        dev = pos.device
+        set_device(dev)
+        pos, nrm = _f32(pos, "dual_loss pos"), _f32(nrm, "dual_loss norm")
+        tgt_vs = require_cuda(tgt_vs, torch.float64, "dual_loss target positions")
+        tgt_fn = require_cuda(tgt_fn, torch.float64, "dual_loss target normals")
+        V, F = topo.V, topo.F
+        if pos.shape != (V, 3) or nrm.shape != (F, 3) or tgt_vs.shape != (V, 3) or tgt_fn.shape != (F, 3):
+            raise RuntimeError("dual_loss: shapes do not match the mesh")
+        nbytes = int(lib.query("ddmp_dual_loss_workspace_bytes", V, F, int(loop)))
+        ws = torch.empty(nbytes // 4, dtype=torch.float32, device=dev)
+        gpos, gnrm = torch.empty_like(pos), torch.empty_like(nrm)
+        losses = torch.empty(6, dtype=torch.float64, device=dev)
+        lib.call("ddmp_dual_loss", ptr(pos), ptr(nrm), ptr(tgt_vs), ptr(tgt_fn), ptr(topo.faces), ptr(topo.f2f),
+                 ptr(topo.rslot), ptr(topo.lap_rowptr), ptr(topo.lap_col), ptr(topo.corner_ptr), ptr(topo.corner_slot),
+                 float(k[0]), float(k[1]), float(k[2]), float(k[3]), float(k[4]), float(bnf_scale), int(loop), ptr(ws),
+                 nbytes, ptr(gpos), ptr(gnrm), ptr(losses), V, F, stream_ptr(dev))
+        ctx.save_for_backward(gpos, gnrm)
+        parts = losses[:5]
+        ctx.mark_non_differentiable(parts)
+        return losses[5], parts
+
+    @staticmethod
+    def backward(ctx, gout, _gparts):
+        gpos, gnrm = ctx.saved_tensors
+        g = gout.to(torch.float32)
+        return gpos * g, gnrm * g, None, None, None, None, None, None
 
 
 class FaceNormals(torch.autograd.Function):

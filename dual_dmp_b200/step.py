@@ -21,7 +21,7 @@ from .util import loss as L
 class DualStep:
     def __init__(self, posnet, normnet, dataset, n_mesh, k=(3.0, 4.0, 4.0, 4.0, 1.0), bnfloop=1, pos_lr=0.01,
                  norm_lr=0.01, grad_clip=0.8, bnf_warmup_epochs=100, capture=True, overlap=True,
-                 fused_optimizer=True):
+                 fused_optimizer=True, fused_loss=True):
         dev = torch.device(posnet.device)
         if dev.type != "cuda":
             raise RuntimeError("DualStep runs on CUDA only (dual_dmp_b200 has no CPU path)")
@@ -39,6 +39,8 @@ class DualStep:
         self.overlap = bool(overlap)
         self._streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev)) if self.overlap else None
         self.fused_optimizer = bool(fused_optimizer)
+        # the five loss calls + weighted sum + their backward as one cooperative kernel (util.loss.dual_loss)
+        self.fused_loss = bool(fused_loss)
         if self.fused_optimizer:       # clip + Adam as two library kernels per network over flat buffers
             self.opt_pos = FusedAdam(posnet, lr=pos_lr)
             self.opt_norm = FusedAdam(normnet, lr=norm_lr, max_norm=self.grad_clip)
@@ -80,14 +82,18 @@ class DualStep:
         else:
             pos = self.posnet(self.dataset)
             nrm = self.normnet(self.dataset)
-        l1 = L.pos_rec_loss(pos, self.tgt_vs)
-        l2 = L.mesh_laplacian_loss(pos, self.mesh)
-        l3 = L.norm_rec_loss(nrm, self.tgt_fn)
-        l4, _ = L.fn_bnf_loss(pos, nrm, self.mesh, loop=self.bnfloop)
-        if bnf_off:
-            l4 = l4 * 0.0                   # still computed and back-propagated, exactly like the reference (:101-102)
-        l5 = L.pos_norm_loss(pos, nrm, self.mesh)
-        loss = k[0] * l1 + k[1] * l2 + k[2] * l3 + k[3] * l4 + k[4] * l5
+        if self.fused_loss:
+            loss, self.parts = L.dual_loss(pos, nrm, self.mesh, self.tgt_vs, self.tgt_fn, k, self.bnfloop,
+                                           0.0 if bnf_off else 1.0)
+        else:
+            l1 = L.pos_rec_loss(pos, self.tgt_vs)
+            l2 = L.mesh_laplacian_loss(pos, self.mesh)
+            l3 = L.norm_rec_loss(nrm, self.tgt_fn)
+            l4, _ = L.fn_bnf_loss(pos, nrm, self.mesh, loop=self.bnfloop)
+            if bnf_off:
+                l4 = l4 * 0.0               # still computed and back-propagated, exactly like the reference (:101-102)
+            l5 = L.pos_norm_loss(pos, nrm, self.mesh)
+            loss = k[0] * l1 + k[1] * l2 + k[2] * l3 + k[3] * l4 + k[4] * l5
         loss.backward()
         if not self.fused_optimizer:
             torch.nn.utils.clip_grad_norm_(self.normnet.parameters(), self.grad_clip)

@@ -89,6 +89,21 @@ def pos_norm_loss(pos: torch.Tensor, norm: torch.Tensor, mesh, ltype="mae") -> t
     return F_.PosNormLoss.apply(pos, norm, topology_for(mesh, pos.device))
 
 
+def dual_loss(pos: torch.Tensor, norm: torch.Tensor, mesh, real_pos, real_norm, k=(3.0, 4.0, 4.0, 4.0, 1.0), bnfloop=1,
+              bnf_scale=1.0):
+    """The five loss calls and the weighted sum of the reference loop body (main.py:94-106) as ONE fused kernel:
+    ``total, parts = dual_loss(pos, norm, n_mesh, n_mesh.vs, n_mesh.fn, (k1..k5), bnfloop, 0.0 if epoch <= 100 else 1.0)``
+    equals ``k1*pos_rec_loss(pos, real_pos) + k2*mesh_laplacian_loss(pos, mesh) + k3*norm_rec_loss(norm, real_norm) +
+    k4*(fn_bnf_loss(pos, norm, mesh, loop=bnfloop)[0] * bnf_scale) + k5*pos_norm_loss(pos, norm, mesh)`` (same
+    arithmetic, same dtypes: ``total`` is float64); ``parts`` holds the five terms.  Not part of the reference API --
+    the drivers' individual calls keep working -- it is what ``dual_dmp_b200.step.DualStep`` runs."""
+    _check_cuda(pos, "dual_loss")
+    _check_cuda(norm, "dual_loss")
+    dev = pos.device
+    return F_.DualLoss.apply(pos, norm, _target64(real_pos, dev), _target64(real_norm, dev), topology_for(mesh, dev),
+                             tuple(float(x) for x in k), int(bnfloop), float(bnf_scale))
+
+
 def mad(norm1: Union[np.ndarray, torch.Tensor], norm2: Union[np.ndarray, torch.Tensor]):
     """reference util/loss.py:261-272.  numpy inputs follow the reference's float64 numpy expression (host-side
     evaluation bookkeeping, reference main.py:60,123); when both are CUDA tensors the fused device reduction is

@@ -61,11 +61,19 @@ int ddmp_gcn_edge_weights(const int32_t* rowptr, const int32_t* col, float* w, i
 /* Y[i,:] = sum_k w[k] * H[col[k],:] (+ bias).  Optional epilogue statistics: stats_partials[b][0][c] = sum of
  * Y[:,c] over row block b, [b][1][c] = sum of Y^2 (BatchNorm partials).  The same call is the backward pass
  * (A_hat is symmetric): dH = spmm(dY) with bias = stats = NULL.  C must be a multiple of 4.
- * amax_blocks (optional, [ddmp_num_row_blocks(n,C)]): max |Y| of every row block, the `amax` input of the dense
- * transforms that consume Y.
+ * amax_blocks (optional, [ddmp_spmm_amax_len(n,C)]): max |Y| of every (row block, channel slice) a CTA produced, the
+ * `amax` input of the dense transforms that consume Y.
+ * Mesh widths (32, 64, multiples of 128 up to 512) run the tile-staged kernel: the row block's own rows of H arrive in
+ * shared memory by one TMA tensor copy, its (rowptr, col, w) stream by coalesced loads (csrc/spmm_tile.cu).
  * [ref: GCNConv.propagate + bias at util/networks.py:51-62,112-123; torch_scatter.scatter_add] */
 int ddmp_spmm_gcn(const int32_t* rowptr, const int32_t* col, const float* w, const float* H, const float* bias,
                   float* Y, float* stats_partials, float* amax_blocks, int64_t n, int32_t C, void* stream);
+/* number of floats ddmp_spmm_gcn writes to amax_blocks for this shape */
+int64_t ddmp_spmm_amax_len(int64_t n, int32_t C);
+/* Kernel choice of ddmp_spmm_gcn (environment DDMP_SPMM_TILE, default 1): 0 = gather-only kernel for every width,
+ * 1 = tile-staged kernel for C <= 128 (where it measures faster on B200), 2 = tile-staged kernel for every mesh width
+ * (A/B measurements, bit-exactness test between the two kernels).  Returns the previous setting. */
+int ddmp_spmm_use_tile_kernel(int mode);
 
 /* Backward aggregation fused with ddmp_bn_bwd_apply:  dH = A_hat * dY  with dY recomputed on the fly from the gathered
  * rows of gX and Y (dY is never materialised); optional colsum_partials[b][0][c] = column sums of dY (conv bias
@@ -74,6 +82,21 @@ int ddmp_spmm_bn_bwd(const int32_t* rowptr, const int32_t* col, const float* w, 
                      const float* mean, const float* rstd, const float* scale, const float* shift, const float* c1,
                      const float* c2, float slope, float* dH, float* colsum_partials, int64_t n, int32_t C,
                      void* stream);
+
+/* The same fusion on the tile-staged kernel (csrc/spmm_tile.cu): the row block's own rows of gX and Y arrive by two TMA
+ * tensor copies, dY of those rows is formed once in shared memory and gathered from there; only references that leave
+ * the block recompute dY from global rows.  Per layer the backward pass then moves 3 tensor passes (+ halo) instead of 5
+ * (ddmp_bn_bwd_apply: read gX, Y, write dY; ddmp_spmm_gcn: read dY, write dH).  colsum_partials (optional):
+ * [ddmp_spmm_bn_bwd_tile_blocks(n,C)][C] column sums of dY per row block (conv-bias gradient); amax_blocks (optional):
+ * [ddmp_spmm_bn_bwd_tile_amax_len(n,C)] max |dH| per CTA.  n may be smaller than the row count of gX / Y (partitioned
+ * mode: [owned | halo] rows, only owned rows are produced).  Symmetric graphs only.
+ * [ref: autograd of nn.BatchNorm1d + nn.LeakyReLU + GCNConv.propagate, util/networks.py:51-62,112-123] */
+int ddmp_spmm_bn_bwd_tile(const int32_t* rowptr, const int32_t* col, const float* w, const float* gX, const float* Y,
+                          const float* mean, const float* rstd, const float* scale, const float* shift,
+                          const float* c1, const float* c2, float slope, float* dH, float* colsum_partials,
+                          float* amax_blocks, int64_t n, int32_t C, void* stream);
+int64_t ddmp_spmm_bn_bwd_tile_blocks(int64_t n, int32_t C);
+int64_t ddmp_spmm_bn_bwd_tile_amax_len(int64_t n, int32_t C);
 
 /* ---- BatchNorm1d (training mode) + LeakyReLU ------------------------------------------------------------ */
 /* partials [nblk][2][C] -> batch mean / biased var; rstd = 1/sqrt(var+eps); scale = gamma*rstd;
@@ -201,6 +224,24 @@ int ddmp_face_normals_fwd(const float* pos, const int32_t* faces, float* fn, int
 int ddmp_face_normals_bwd(const float* pos, const int32_t* faces, const int32_t* corner_ptr,
                           const int32_t* corner_slot, const float* gfn, float* face_tmp, float* gpos, int64_t V,
                           int64_t F, void* stream);
+/* The whole loss phase of one iteration as ONE cooperative launch (csrc/loss_fused.cu): the five losses with the
+ * reference's weights, total = k1*pos_rec + k2*laplacian + k3*norm_rec + k4*(bnf*bnf_scale) + k5*pos_norm, and its
+ * gradients gpos [V,3] = d total / d pos, gnrm [F,3] = d total / d norm (for an upstream gradient of 1).  bnf_scale is
+ * the reference's `loss_norm2 * 0.0` while epoch <= 100 (1.0 afterwards): the term is still evaluated and its
+ * gradient multiplied by it.  losses [6] (float64): the five terms as the reference computes them (float64 for
+ * pos_rec / norm_rec, float32 values for the others) and the weighted total.  Same arithmetic as the stand-alone
+ * kernels above; phases that need a mesh-wide scalar or neighbour values of the previous phase are separated by
+ * grid-wide barriers instead of kernel boundaries.  rslot [F,3]: position of face f in the f2f row of its neighbour.
+ * workspace: ddmp_dual_loss_workspace_bytes(V, F, loop) bytes, contents irrelevant on entry.
+ * [ref: main.py:94-106 (loss calls, warm-up switch, weighted sum) + loss.backward() at :107; util/loss.py:16-160] */
+int64_t ddmp_dual_loss_workspace_bytes(int64_t V, int64_t F, int32_t loop);
+int ddmp_dual_loss(const float* pos, const float* nrm, const double* tgt_vs, const double* tgt_fn,
+                   const int32_t* faces, const int32_t* f2f, const int32_t* rslot, const int32_t* lap_rowptr,
+                   const int32_t* lap_col, const int32_t* corner_ptr, const int32_t* corner_slot, float k1, float k2,
+                   float k3, float k4, float k5, float bnf_scale, int32_t loop, void* workspace,
+                   int64_t workspace_bytes, float* gpos, float* gnrm, double* losses, int64_t V, int64_t F,
+                   void* stream);
+
 /* mean angular distance in degrees between two sets of unit normals, float64 [ref: util/loss.py:261-272]. */
 int ddmp_mad(const float* n1, const float* n2, double* out, void* scratch, int64_t F, void* stream);
 /* vertex normals: normalise(sum of incident face normals) through the corner CSR [ref: util/models.py:12-29]. */

@@ -57,7 +57,7 @@ def test_graph_is_bit_exact_and_weights_match(graphs, kind):
         assert np.array_equal(perm, np.arange(graph.n))
 
 
-@pytest.mark.parametrize("C", [32, 64, 128, 256, 512, 12, 3])
+@pytest.mark.parametrize("C", [32, 64, 128, 256, 512, 384, 12, 3])
 @pytest.mark.parametrize("which", ["vg_id", "fg_id"])
 def test_spmm_matches_oracle(graphs, C, which):
     from dual_dmp_b200 import functional as F_
@@ -398,3 +398,81 @@ def test_fused_bn_backward_aggregation(graphs, C, which):
 def GcnGraphIdentity(n):
     from dual_dmp_b200.graph import GcnGraph
     return GcnGraph(torch.zeros(2, 0, dtype=torch.long), n, DEV, reorder=False)
+
+
+@pytest.mark.parametrize("C", [32, 64, 128, 256, 512])
+@pytest.mark.parametrize("kind,n", [("ico", 3), ("ico", 10), ("open", 9), ("ico", 40)])
+def test_spmm_tile_kernel_equals_gather_kernel_bitwise(kind, n, C):
+    """csrc/spmm_tile.cu (TMA-staged row block + shared-memory index stream) against csrc/spmm.cu (gathers only): the
+    two accumulate every row in the same CSR order, so Y, the BatchNorm partial sums and max|Y| must be IDENTICAL --
+    closed and open meshes, Morton-ordered and caller-ordered graphs, row counts below / not a multiple of the row
+    block, and the partitioned layout (H = [owned | halo] rows, only the owned rows computed)."""
+    from dual_dmp_b200 import functional as F_
+    from dual_dmp_b200._lib import lib
+    from dual_dmp_b200.graph import GcnGraph
+    from oracle.step_ref import make_dataset
+    n_mesh, s_mesh, _ = small_case(kind, n)
+    ds = make_dataset(n_mesh, s_mesh)
+    V, F = len(n_mesh.vs), len(n_mesh.faces)
+    graphs_ = [GcnGraph(ds.edge_index, V, DEV, coords=ds.x_pos, reorder=True),
+               GcnGraph(ds.face_index, F, DEV, coords=ds.z2.detach()[:, :3], reorder=True),
+               GcnGraph(ds.face_index, F, DEV, reorder=False)]
+    torch.manual_seed(C + n)
+    try:
+        for graph in graphs_:
+            H = torch.randn(graph.n, C, device=DEV)
+            b = torch.randn(C, device=DEV)
+            res = {}
+            for on in (2, 0):
+                lib.query("ddmp_spmm_use_tile_kernel", on)
+                Y, partials, ab = F_.spmm_gcn(graph, H, bias=b, stats=True, amax=True)
+                Yp = F_.spmm_gcn(graph, H)
+                res[on] = (Y, partials, ab.max(), Yp)
+            assert torch.equal(res[2][0], res[0][0]) and torch.equal(res[2][3], res[0][3])
+            assert torch.equal(res[2][1], res[0][1])
+            assert float(res[2][2]) == float(res[0][2]) == float(res[0][0].abs().max())
+            # partitioned layout: the last rows of H are "halo" rows that are only read
+            n_own = graph.n - max(1, graph.n // 7)
+            rp = graph.rowptr[: n_own + 1].contiguous()
+            sub = type("G", (), dict(rowptr=rp, col=graph.col, w=graph.w, rowptr_t=rp, col_t=graph.col, w_t=graph.w))
+            outs = []
+            for on in (2, 0):
+                lib.query("ddmp_spmm_use_tile_kernel", on)
+                outs.append(F_.spmm_gcn(sub, H, bias=b, n_rows=n_own))
+            assert outs[0].shape == (n_own, C) and torch.equal(outs[0], outs[1])
+            assert torch.equal(outs[0], res[0][0][:n_own])
+    finally:
+        lib.query("ddmp_spmm_use_tile_kernel", 1)
+
+
+@pytest.mark.parametrize("C", [32, 64, 128, 256, 384, 512])
+@pytest.mark.parametrize("kind,n,which", [("open", 9, "vg"), ("open", 9, "fg"), ("ico", 3, "fg"), ("ico", 24, "vg"),
+                                          ("ico", 24, "fg_id")])
+def test_tile_fused_bn_backward_aggregation(kind, n, which, C):
+    """ddmp_spmm_bn_bwd_tile (dY formed in shared memory from TMA-staged gX / Y tiles, never written to HBM) ==
+    ddmp_bn_bwd_apply followed by ddmp_spmm_gcn, including the conv-bias gradient (column sums of dY) and max|dH|"""
+    from dual_dmp_b200 import functional as F_
+    from dual_dmp_b200.graph import GcnGraph
+    from oracle.step_ref import make_dataset
+    n_mesh, s_mesh, _ = small_case(kind, n)
+    ds = make_dataset(n_mesh, s_mesh)
+    if which == "vg":
+        g = GcnGraph(ds.edge_index, len(n_mesh.vs), DEV, coords=ds.x_pos, reorder=True)
+    else:
+        g = GcnGraph(ds.face_index, len(n_mesh.faces), DEV, coords=ds.z2.detach()[:, :3], reorder=which == "fg")
+    torch.manual_seed(C + n)
+    rows = g.n
+    Y = (torch.randn(rows, C) * 1.5 + 0.3).to(DEV)
+    gX = torch.randn(rows, C, device=DEV)
+    st = F_.bn_stats_finalize(F_.spmm_gcn(GcnGraphIdentity(rows), Y, stats=True)[1], rows,
+                              (torch.rand(C) + 0.5).to(DEV), torch.randn(C).to(DEV))
+    dY, dgamma, dbeta, dbias = F_.bn_lrelu_backward(gX, Y, st)
+    dH_ref = F_.spmm_gcn(g, dY, transposed=True)
+    dH, dgamma2, dbeta2, dbias2, ab = F_.bn_bwd_spmm_tile(g, gX, Y, st, amax=True)
+    e = rel_err(dH, dH_ref)
+    report(f"tile-fused bn+spmm bwd C={C} {kind}{n} {which}", e)
+    assert e < 2e-6 and torch.equal(dgamma, dgamma2) and torch.equal(dbeta, dbeta2)
+    assert (dbias2 - dbias).abs().max() <= 1e-5 * dY.abs().sum(dim=0).max()
+    assert float(ab.max()) == float(dH.abs().max())
+    a, _, _, _, _ = F_.bn_bwd_spmm_tile(g, gX, Y, st)
+    assert torch.equal(a, dH)                                                   # deterministic
