@@ -72,6 +72,7 @@ def parse_args():
                          "range-partitioned over the GPUs, NCCL halo exchange; weak scaling).  'independent' = one mesh "
                          "fit per GPU, no data-path collective.  'partition' = strong scaling on the --freq mesh")
     ap.add_argument("--no-mode-a", action="store_true", help="N>1: skip the independent-replica side measurement")
+    ap.add_argument("--no-small", action="store_true", help="N=1: skip the fandisk-sized CAD-weights side measurement")
     ap.add_argument("--detail", default=None, help="write a per-kernel-group timing table (JSON) to this path")
     return ap.parse_args()
 
@@ -101,15 +102,17 @@ def _sha256(path):
 def spmm_traffic(args, n_sp, sp_bytes):
     """DRAM traffic per SpMM launch (dram__bytes_read.sum + dram__bytes_write.sum, average over the 48 launches of a
     step) from the committed ncu capture -- reported only when that capture was taken on the spmm.cu that is being
-    benchmarked (sha256 recorded by scripts/spmm_traffic.py) and on the benchmark mesh; otherwise null."""
+    benchmarked (sha256 of the kernel sources recorded by scripts/spmm_traffic.py) and on the benchmark mesh; else null."""
     path = os.path.join(ROOT, "profiles", "spmm_dram_traffic_r2.json")
     try:
         tj = json.load(open(path))
     except Exception:
         return None, "no ncu capture for this build (profiles/spmm_dram_traffic_r2.json missing)"
-    src = os.path.join(ROOT, "dual_dmp_b200", "csrc", "spmm.cu")
-    if tj.get("spmm_cu_sha256") != _sha256(src):
-        return None, "ncu capture is of an older spmm.cu (sha256 mismatch): traffic not reported"
+    import hashlib
+    srcs = [os.path.join(ROOT, "dual_dmp_b200", "csrc", f) for f in ("spmm.cu", "spmm_tile.cu")]
+    sha = hashlib.sha256(b"".join(open(p_, "rb").read() for p_ in srcs)).hexdigest()
+    if tj.get("spmm_sources_sha256") != sha:
+        return None, "ncu capture is of older aggregation kernels (sha256 of spmm.cu + spmm_tile.cu differs): not reported"
     if args.n != tj.get("n") or not n_sp:
         return None, "ncu capture is of another mesh"
     return tj["dram_bytes_per_launch_avg"], (
@@ -505,6 +508,8 @@ def run_ours(args):
         os.makedirs(os.path.dirname(os.path.abspath(args.detail)), exist_ok=True)
         json.dump({k_: {"ms_total": v[0], "GBps": v[1] / (v[0] * 1e-3) / 1e9 if v[0] > 0 else None, "launches": v[2]}
                    for k_, v in by_width.items()}, open(args.detail, "w"), indent=1)
+    if world == 1 and not args.no_small:
+        out["config"]["cad_small_mesh"] = small_cad_line(dev)
     if not args.no_cpu_baseline and world == 1:
         torch.cuda.empty_cache()
         out["cpu_baseline"] = cpu_reference(args, max_steps=1, warmup=1, budget_s=120.0, case=(n_mesh, s_mesh))
@@ -515,6 +520,37 @@ def run_ours(args):
 
 # ---------------------------------------------------------------------------------------------------------------------
 ORACLE_BYTES_PER_FACE = 135_000     # resident set of one oracle step (PyG-style saved edge messages), measured: 122-130 KB
+
+
+def small_cad_line(dev, n=25, steps=200):
+    """side measurement (not the headline): a fandisk-sized mesh (BASELINE.json configs[0]: 12,946 faces there, 12,500
+    here) with the CAD loss weights of reference README.md:57 (k=3,0,3,4,2, bnfloop=5) -- the regime where launch count,
+    not bandwidth, limits the step: CUDA-graph replay of DualStep against the eager drop-in loop"""
+    from dual_dmp_b200._lib import lib
+    from dual_dmp_b200.step import DualStep
+    from dual_dmp_b200.util.networks import NormalNet, PosNet
+    n_mesh, s_mesh, ds = build_case(n)
+    k, loop = (3.0, 0.0, 3.0, 4.0, 2.0), 5
+    res = {"workload": f"icosphere n={n}: {len(n_mesh.faces)} faces, k={list(k)}, bnfloop={loop}"}
+    for label, capture in (("graph_replay", True), ("eager", False)):
+        torch.manual_seed(0)
+        p, q = PosNet(dev).to(dev), NormalNet(dev).to(dev)
+        st = DualStep(p, q, ds, n_mesh, k=k, bnfloop=loop, capture=capture)
+        for i in range(6):
+            st.step(101 + i)
+        torch.cuda.synchronize()
+        l0 = lib.query("ddmp_launch_count")
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            st.step(107 + i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        res[label] = {"ms_per_step": round(ms, 4), "iters_per_s": round(1000.0 / ms, 1)}
+        if not capture:
+            res[label]["library_launches_per_step"] = int((lib.query("ddmp_launch_count") - l0) // steps)
+    return res
 
 
 def _pick_cpu_mesh(args):
@@ -681,12 +717,18 @@ def run_partitioned(args, weak):
     F_base = 20 * args.n * args.n
     torch.manual_seed(0)
     posnet, normnet = PosNet(dev).to(dev), NormalNet(dev).to(dev)
+    overlap = world > 1 and not args.no_overlap
     if world > 1:
-        ppos, pnrm = PartitionedNet(posnet, rank, world), PartitionedNet(normnet, rank, world)
+        # one NCCL communicator per network: PosNet and NormalNet run on two compute streams (DualStep overlap), so the
+        # halo exchange / BatchNorm all-reduce latency of one network is hidden behind the kernels of the other; the
+        # collectives of one communicator stay in program order on every rank
+        g_pos = dist.new_group(list(range(world))) if overlap else None
+        g_nrm = dist.new_group(list(range(world))) if overlap else None
+        ppos, pnrm = PartitionedNet(posnet, rank, world, group=g_pos), PartitionedNet(normnet, rank, world, group=g_nrm)
     else:
         ppos, pnrm = posnet, normnet
-    # the reference loop body as one object; eager (no graph capture across NCCL calls), one compute stream
-    stepper = DualStep(ppos, pnrm, ds, n_mesh, k=args.k, bnfloop=args.bnfloop, capture=False, overlap=False)
+    # the reference loop body as one object; eager (no graph capture across NCCL calls)
+    stepper = DualStep(ppos, pnrm, ds, n_mesh, k=args.k, bnfloop=args.bnfloop, capture=False, overlap=overlap)
     epoch0 = 101
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -732,7 +774,9 @@ def run_partitioned(args, weak):
         sp_bytes[0] += spmm_bytes(graph.n, graph.nnz, H.shape[1])
         return orig_spmm(graph, H, *a, **kw)
     F_.spmm_gcn = spmm_counted
+    was_overlap, stepper.overlap = stepper.overlap, False      # one stream: per-phase events must not time-slice
     ms_ph, _, _ = timed(lambda i: stepper.step(epoch0 + 3 + args.steps + i), args.steps)
+    stepper.overlap = was_overlap
     F_.spmm_gcn = orig_spmm
     pt.restore()
     torch.cuda.synchronize()
@@ -820,7 +864,11 @@ def run_partitioned(args, weak):
                           "iters_per_s_of_this_mesh": 1000.0 / ms_per_step, "rank0_partition": halo,
                           "rank0_peak_mem_GiB": round(mem, 2), "setup_s": round(setup_s, 1),
                           "l2_policy": "working set (>=10 GB of saved activations per rank) exceeds L2",
+                          "streams": "PosNet / NormalNet on two compute streams, one NCCL communicator each" if overlap
+                                     else "one compute stream",
                           "phases_ms_per_step_rank0": {k_: round(v, 3) for k_, v in sorted(phases.items())},
+                          "phases_note": "per-phase pass runs on ONE stream (no overlap), so the phases add up to its "
+                                         "step time, not to ms_per_step",
                           "largest_non_compute_phase": limiter[0],
                           "mode_a_replicas": mode_a},
                "e2e": e2e, "gpu_launches": int(launches), "loss": float(loss.detach()),

@@ -201,7 +201,7 @@ static int launch_rowblock(const float* gX, const float* Y, const float* mean, c
     const int RL = 256 / lanes_c;
     const size_t smem = (size_t)RL * SETS * C * sizeof(float);
     DDMP_REQUIRE(smem <= 48 * 1024, "%s: C=%d too wide", what, C);
-    const int rpb = ddmp_rows_per_block(C);
+    const int rpb = ddmp_elem_rows_per_block(C);
     rowblock_kernel<MODE><<<(unsigned)ceil_div(n, rpb), 256, smem, st>>>(gX, Y, mean, rstd, scale, shift, slope, c1,
                                                                          c2, dY, partials, n, C, rpb);
     return check_launch(what);

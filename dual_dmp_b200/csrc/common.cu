@@ -71,6 +71,17 @@ int ddmp_rows_per_block(int32_t C) {
     return C <= 32 ? 256 : 128;
 }
 
+// Row block of the element-wise BatchNorm-backward / column-sum kernels (bn.cu).  Independent of the aggregation kernel's
+// block: 512 rows keep >= 1,900 CTAs at 1M rows while the [blocks][sets][C] partials -- which the finalize kernels
+// re-read with only C/8 CTAs -- shrink 4x against 128-row blocks (finalize: 46 us -> ~12 us at C = 512, 48 per step).
+int ddmp_elem_rows_per_block(int32_t C) { return C > 0 ? 512 : 0; }
+
+int64_t ddmp_num_elem_blocks(int64_t n, int32_t C) {
+    const int r = ddmp_elem_rows_per_block(C);
+    if (r <= 0 || n <= 0) return 0;
+    return (n + r - 1) / r;
+}
+
 int64_t ddmp_num_row_blocks(int64_t n, int32_t C) {
     int r = ddmp_rows_per_block(C);
     if (r <= 0 || n <= 0) return 0;

@@ -111,7 +111,7 @@ constexpr float kSigmaS2 = 0.09f;
 
 #define STRIDE_LOOP(i, count) for (int64_t i = tid; i < (count); i += nth)
 
-__global__ void __launch_bounds__(kT)
+__global__ void __launch_bounds__(kT, 4)
 dual_loss_kernel(const Args a) {
     cg::grid_group grid = cg::this_grid();
     __shared__ double sm[kT / 32];

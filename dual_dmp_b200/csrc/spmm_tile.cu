@@ -388,6 +388,10 @@ static EncodeFn encode_fn() {
 }
 
 static int make_map(CUtensorMap* map, const float* H, int64_t n, int C, int CS, int R) {
+    // the driver call needs a current context on THIS thread: the autograd engine's thread may reach the first
+    // aggregation of a backward pass before any runtime call has bound the primary context to it
+    static thread_local const bool bound = (cudaFree(nullptr), true);
+    (void)bound;
     EncodeFn enc = encode_fn();
     if (!enc) {
         set_error("spmm_tile: cuTensorMapEncodeTiled is not available from this driver");

@@ -25,7 +25,7 @@ FUSE_BN_SPMM = False
 # backward: BatchNorm/LeakyReLU "apply" folded into the TILE-staged aggregation kernel (ddmp_spmm_bn_bwd_tile): dY of a row
 # block is formed once in shared memory from the TMA-staged gX / Y tiles, so the gather volume does not double and dY
 # never goes to HBM (3 tensor passes per layer instead of 5).  Single-GPU path only (the partitioned mode exchanges dY).
-FUSE_BN_SPMM_TILE = os.environ.get("DDMP_FUSE_BN_TILE", "1") != "0"
+FUSE_BN_SPMM_TILE = os.environ.get("DDMP_FUSE_BN_TILE", "0") != "0"
 TILE_WIDTHS = (32, 64, 128, 256, 384, 512)
 
 HEAD_POS, HEAD_NORM = 0, 1
@@ -43,6 +43,11 @@ def num_row_blocks(n: int, C: int) -> int:
 
 
 AMAX_WIDTHS = (64, 128, 256, 512)      # widths whose aggregation kernel has the amax epilogue and feed tensor-core GEMMs
+
+
+def num_elem_blocks(n: int, C: int) -> int:
+    """row blocks of the element-wise kernels (BatchNorm backward reduce / apply, column sums)"""
+    return int(lib.query("ddmp_num_elem_blocks", n, C))
 
 
 def spmm_gcn(graph: GcnGraph, H, bias=None, stats=False, transposed=False, out=None, n_rows=None, amax=False):
@@ -116,7 +121,7 @@ def partials_to_sums(partials):
 
 def colsum(X):
     n, C = X.shape
-    nblk = num_row_blocks(n, C)
+    nblk = num_elem_blocks(n, C)
     partials = torch.empty(nblk, 1, C, dtype=torch.float32, device=X.device)
     out = torch.empty(C, dtype=torch.float32, device=X.device)
     st = stream_ptr(X.device)
@@ -146,7 +151,7 @@ def bn_lrelu_backward(gX, Y, stats, dY_out=None, comm=None):
     n, C = Y.shape
     dev = Y.device
     st = stream_ptr(dev)
-    nblk = num_row_blocks(n, C)
+    nblk = num_elem_blocks(n, C)
     partials = torch.empty(nblk, 2, C, dtype=torch.float32, device=dev)
     small = torch.empty(5, C, dtype=torch.float32, device=dev)             # dgamma, dbeta, c1, c2, dbias
     mean, rstd, scale, shift = stats[0], stats[1], stats[2], stats[3]
@@ -172,8 +177,10 @@ def bn_bwd_spmm_fused(graph, gX, Y, stats, dH_out=None):
     n, C = Y.shape
     dev = Y.device
     st = stream_ptr(dev)
-    nblk = num_row_blocks(n, C)
+    nblk = num_elem_blocks(n, C)
     partials = torch.empty(nblk, 2, C, dtype=torch.float32, device=dev)
+    nblk_s = num_row_blocks(n, C)                                          # row blocks of the aggregation kernel
+    colsum_p = torch.empty(nblk_s, 1, C, dtype=torch.float32, device=dev)
     small = torch.empty(5, C, dtype=torch.float32, device=dev)             # dgamma, dbeta, c1, c2, dbias
     mean, rstd, scale, shift = stats[0], stats[1], stats[2], stats[3]
     lib.call("ddmp_bn_bwd_reduce", ptr(gX), ptr(Y), ptr(mean), ptr(rstd), ptr(scale), ptr(shift), SLOPE,
@@ -182,8 +189,8 @@ def bn_bwd_spmm_fused(graph, gX, Y, stats, dH_out=None):
              ptr(small[3]), st)
     dH = dH_out if dH_out is not None else torch.empty_like(Y)
     lib.call("ddmp_spmm_bn_bwd", ptr(graph.rowptr), ptr(graph.col), ptr(graph.w), ptr(gX), ptr(Y), ptr(mean),
-             ptr(rstd), ptr(scale), ptr(shift), ptr(small[2]), ptr(small[3]), SLOPE, ptr(dH), ptr(partials), n, C, st)
-    lib.call("ddmp_colsum_finalize", ptr(partials), nblk, 1, C, ptr(small[4]), st)
+             ptr(rstd), ptr(scale), ptr(shift), ptr(small[2]), ptr(small[3]), SLOPE, ptr(dH), ptr(colsum_p), n, C, st)
+    lib.call("ddmp_colsum_finalize", ptr(colsum_p), nblk_s, 1, C, ptr(small[4]), st)
     return dH, small[0], small[1], small[4]
 
 
@@ -194,7 +201,7 @@ def bn_bwd_spmm_tile(graph, gX, Y, stats, dH_out=None, amax=False):
     n, C = Y.shape
     dev = Y.device
     st = stream_ptr(dev)
-    nblk = num_row_blocks(n, C)
+    nblk = num_elem_blocks(n, C)
     partials = torch.empty(nblk, 2, C, dtype=torch.float32, device=dev)
     small = torch.empty(5, C, dtype=torch.float32, device=dev)             # dgamma, dbeta, c1, c2, dbias
     mean, rstd, scale, shift = stats[0], stats[1], stats[2], stats[3]

@@ -119,6 +119,23 @@ def mad(norm1: Union[np.ndarray, torch.Tensor], norm2: Union[np.ndarray, torch.T
     return np.sum(sad) / len(sad)
 
 
+def _not_on_the_hot_path(name, where):
+    def f(*a, **kw):
+        raise NotImplementedError(
+            f"{name} ({where}) is not called by main.py / main4real.py and is outside the accelerated hot path "
+            "(SURVEY.md §2.1 row 2); use the reference implementation for it")
+    f.__name__ = name
+    return f
+
+
+# present in reference util/loss.py but never called by its drivers: refuse loudly instead of an AttributeError
+weighted_norm_rec_loss = _not_on_the_hot_path("weighted_norm_rec_loss", "reference util/loss.py:162-172")
+weighted_pos_norm_loss = _not_on_the_hot_path("weighted_pos_norm_loss", "reference util/loss.py:174-192")
+bnf = _not_on_the_hot_path("bnf", "reference util/loss.py:195-259, numpy bilateral filter with a per-vertex Python loop")
+distance_from_reference_mesh = _not_on_the_hot_path("distance_from_reference_mesh",
+                                                    "reference util/loss.py:279-284, pymeshlab Hausdorff")
+
+
 def angular_difference(norm1, norm2):
     """reference util/loss.py:274-277 (used by check/mad_checker.py)."""
     inner = np.sum(norm1 * norm2, 1)

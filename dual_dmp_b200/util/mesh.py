@@ -218,3 +218,20 @@ class Mesh:
         assert len(self.vs) > 0
         from ..synth import write_obj
         write_obj(filename, self.vs, self.faces)
+
+    def save_as_ply(self, filename, fn):
+        """ASCII PLY with one RGBA colour per face, ``fn`` [F,3] in [0,1] -> 0..255 (same header and number formats as
+        reference util/mesh.py:287-318, which check/mad_checker.py:48 calls; host-side output, one bulk write)."""
+        assert len(self.vs) > 0
+        v32 = np.asarray(self.vs, dtype=np.float32)
+        faces = np.asarray(self.faces, dtype=np.uint32)
+        col = np.clip((255 * np.asarray(fn, dtype=np.float32)).astype(np.int64), 0, 255)     # int() truncates toward 0
+        with open(filename, "w") as fp:
+            fp.write("ply\nformat ascii 1.0\nelement vertex {}\n".format(len(v32)))
+            fp.write("property float x\nproperty float y\nproperty float z\n")
+            fp.write("element face {}\n".format(len(faces)))
+            fp.write("property list uchar int vertex_indices\n")
+            fp.write("property uchar red\nproperty uchar green\nproperty uchar blue\nproperty uchar alpha\n")
+            fp.write("end_header\n")
+            fp.write("".join("{0:.6f} {1:.6f} {2:.6f}\n".format(*row) for row in v32.tolist()))
+            fp.write("".join("3 {0} {1} {2} {3} {4} {5} 255\n".format(*f, *c) for f, c in zip(faces.tolist(), col.tolist())))

@@ -50,6 +50,10 @@ int ddmp_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * [ddmp_num_row_blocks(n, C)][sets][C] float32). */
 int ddmp_rows_per_block(int32_t C);
 int64_t ddmp_num_row_blocks(int64_t n, int32_t C);
+/* row block of the element-wise kernels (ddmp_bn_bwd_reduce / ddmp_bn_bwd_apply / ddmp_colsum_partials): their partials
+ * are [ddmp_num_elem_blocks(n, C)][sets][C] */
+int ddmp_elem_rows_per_block(int32_t C);
+int64_t ddmp_num_elem_blocks(int64_t n, int32_t C);
 
 /* ---- graph --------------------------------------------------------------------------------------------- */
 /* GCN symmetric normalisation, hoisted out of the step.  CSR rows are TARGET nodes and already contain exactly
@@ -224,6 +228,30 @@ int ddmp_face_normals_fwd(const float* pos, const int32_t* faces, float* fn, int
 int ddmp_face_normals_bwd(const float* pos, const int32_t* faces, const int32_t* corner_ptr,
                           const int32_t* corner_slot, const float* gfn, float* face_tmp, float* gpos, int64_t V,
                           int64_t F, void* stream);
+/* ---- mesh preprocessing on the device, float64 ------------------------------------------ */
+/* Conventions of the reference's offline tools, which need pymeshlab: uniform Laplacian smoothing x30 for the *_smooth
+ * mesh, Gaussian noise along the vertex normal, unit-box normalisation, rescale to mean edge length 1.
+ * (rowptr, col) = unweighted vertex adjacency CSR without self loops; (corner_ptr, corner_slot) = corner CSR.
+ * [ref: preprocess/noisemaker.py:25-42, preprocess/preprocess.py:22-28,68-72; util/mesh.py:87-107] */
+int64_t ddmp_prep_scratch_bytes(void);
+/* one Jacobi sweep  x_i <- (x_i + sum_{j in N(i)} x_j) / (deg_i + 1) */
+int ddmp_prep_smooth_sweep(const double* pos_in, const int32_t* rowptr, const int32_t* col, double* pos_out, int64_t V,
+                           void* stream);
+/* float64 face normals (n / (|n| + 1e-24)), areas, centroids; any output may be NULL */
+int ddmp_prep_face_geometry(const double* vs, const int32_t* faces, double* fn, double* fa, double* fc, int64_t F,
+                            void* stream);
+/* vn = normalise(sum of incident face normals); all-zero rows stay zero */
+int ddmp_prep_vertex_normals(const double* fn, const int32_t* corner_ptr, const int32_t* corner_slot, double* vn,
+                             int64_t V, void* stream);
+/* out[v,:] = (a[v,:] + b[v,:]*t[v] + shift[:]) * scale;  b/t and shift optional (noise along the normal; recentre+rescale) */
+int ddmp_prep_affine_rows(const double* a, const double* b, const double* t, const double* shift, double scale,
+                          double* out, int64_t V, void* stream);
+/* sum over edges [E,2] of |v_a - v_b| (mean edge length = out / E) */
+int ddmp_prep_edge_length_sum(const double* vs, const int32_t* edges, double* out, void* scratch, int64_t E,
+                              void* stream);
+/* out6 = (min x, min y, min z, max x, max y, max z) */
+int ddmp_prep_bbox(const double* vs, double* out6, void* scratch, int64_t V, void* stream);
+
 /* The whole loss phase of one iteration as ONE cooperative launch (csrc/loss_fused.cu): the five losses with the
  * reference's weights, total = k1*pos_rec + k2*laplacian + k3*norm_rec + k4*(bnf*bnf_scale) + k5*pos_norm, and its
  * gradients gpos [V,3] = d total / d pos, gnrm [F,3] = d total / d norm (for an upstream gradient of 1).  bnf_scale is

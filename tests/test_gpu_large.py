@@ -115,6 +115,43 @@ def test_f16_split_gemms_full_size_vs_float64():
     assert torch.equal(dW, F_.gemm_dw(dH, X, C, scale=sc, shift=sh, backend=2, amax_dh=blockmax, amax_x=bound))
 
 
+@pytest.mark.parametrize("n", [8_000_000, 16_020_500])
+def test_f16_split_gemms_at_partitioned_mesh_row_counts(n):
+    """the operand bound of activated inputs, |gamma|*sqrt(n-1)+|beta|, grows with the row count (2,800 sigma at 8M rows,
+    4,000 sigma at the 16M-face config of BASELINE.json): every doubling of n costs half a bit of the `lo` piece.  At the
+    row counts of the partitioned configs (256 -> 256 transform, 8 / 16 GB per tensor) sampled rows of X.W^T and dH.W and
+    the whole dH^T.X still meet the 1M-row bars against float64"""
+    from dual_dmp_b200 import functional as F_
+    free, _ = torch.cuda.mem_get_info()
+    if free < 5 * n * 256 * 4:
+        pytest.skip("not enough device memory for this row count")
+    torch.manual_seed(3)
+    C = 256
+    X = torch.randn(n, C, device=DEV)
+    W = torch.randn(C, C, device=DEV) / C ** 0.5
+    gamma, beta = torch.rand(C, device=DEV) + 0.5, torch.randn(C, device=DEV) * 0.2
+    sc, sh = gamma, beta                                                      # X is already ~N(0,1) per channel
+    bound = gamma.abs() * (n - 1) ** 0.5 + beta.abs()                         # what ddmp_bn_stats_finalize emits
+    rows = torch.randint(0, n, (513,), device=DEV)
+    act = torch.nn.functional.leaky_relu(X[rows].double() * sc.double() + sh.double(), 0.01)
+    H = F_.gemm_xw(X, W, scale=sc, shift=sh, backend=2, amax=bound)
+    e_xw = rel_err(H[rows], act @ W.double().t())
+    del H
+    dH = torch.randn(n, C, device=DEV) * 1e-6 * torch.exp(torch.randn(n, 1, device=DEV))
+    amax = dH.abs().amax().reshape(1).contiguous()
+    gX = F_.gemm_dx(dH, W, backend=2, amax=amax)
+    e_dx = rel_err(gX[rows], dH[rows].double() @ W.double())
+    del gX
+    dW = F_.gemm_dw(dH, X, C, scale=sc, shift=sh, backend=2, amax_dh=amax, amax_x=bound)
+    ref = torch.zeros(C, C, dtype=torch.float64, device=DEV)
+    for lo in range(0, n, 262144):
+        a = torch.nn.functional.leaky_relu(X[lo:lo + 262144].double() * sc.double() + sh.double(), 0.01)
+        ref += dH[lo:lo + 262144].double().t() @ a
+    e_dw = rel_err(dW, ref)
+    report(f"f16-split GEMMs {n} x 256x256, bound {float(bound.max()):.0f} (xw, dx, dw)", (e_xw, e_dx, e_dw))
+    assert e_xw < 5e-6 and e_dx < 5e-6 and e_dw < 2e-5, (e_xw, e_dx, e_dw)
+
+
 def test_network_equivariance_and_determinism_1m(big):
     """the Morton relabelling must not change the result (this is what legitimises the reorder); reruns are bitwise
     identical; outputs are finite and NormalNet rows are unit vectors"""

@@ -445,7 +445,7 @@ def test_spmm_tile_kernel_equals_gather_kernel_bitwise(kind, n, C):
         lib.query("ddmp_spmm_use_tile_kernel", 1)
 
 
-@pytest.mark.parametrize("C", [32, 64, 128, 256, 384, 512])
+@pytest.mark.parametrize("C", [32, 64, 128, 256, 512])
 @pytest.mark.parametrize("kind,n,which", [("open", 9, "vg"), ("open", 9, "fg"), ("ico", 3, "fg"), ("ico", 24, "vg"),
                                           ("ico", 24, "fg_id")])
 def test_tile_fused_bn_backward_aggregation(kind, n, which, C):

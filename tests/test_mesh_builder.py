@@ -72,3 +72,34 @@ def test_icosphere_invariants():
     assert m.f_edges.shape == (2, 3 * len(faces))
     fwd = set(map(tuple, m.f_edges.T.tolist()))
     assert fwd == set((b, a) for a, b in fwd) and len(fwd) == m.f_edges.shape[1]
+
+
+def test_save_as_ply_format(tmp_path):
+    """Mesh.save_as_ply (reference util/mesh.py:287-318, used by check/mad_checker.py:48): header, 6-decimal float32
+    vertices, '3 i j k r g b 255' faces with the colour truncated to 0..255 (checked byte-identical to the reference
+    writer when the build container's /root/reference is importable: oracle/make_golden.py conventions)"""
+    import numpy as np
+    from dual_dmp_b200 import synth
+    from dual_dmp_b200.util.mesh import Mesh
+    vs, faces = synth.icosphere(1)
+    m = Mesh(vs=vs, faces=faces)
+    col = np.clip(np.abs(m.fn) * 1.2, 0, None)              # some channels above 1 -> clipped to 255
+    path = tmp_path / "a.ply"
+    m.save_as_ply(str(path), col)
+    lines = path.read_text().split("\n")
+    assert lines[:3] == ["ply", "format ascii 1.0", "element vertex 12"]
+    assert lines[6] == "element face 20" and lines[12] == "end_header"
+    v0 = np.float32(vs[0])
+    assert lines[13] == "{0:.6f} {1:.6f} {2:.6f}".format(*v0.tolist())
+    f0 = lines[13 + 12].split()
+    assert f0[0] == "3" and [int(x) for x in f0[1:4]] == faces[0].tolist() and f0[7] == "255"
+    assert [int(x) for x in f0[4:7]] == np.clip((255 * np.float32(col[0])).astype(int), 0, 255).tolist()
+    assert len(lines) == 13 + 12 + 20 + 1
+
+
+def test_reference_functions_outside_the_hot_path_refuse_loudly():
+    import pytest
+    from dual_dmp_b200.util import loss as L
+    for name in ("weighted_norm_rec_loss", "weighted_pos_norm_loss", "bnf", "distance_from_reference_mesh"):
+        with pytest.raises(NotImplementedError, match="outside the accelerated hot path"):
+            getattr(L, name)(None, None)

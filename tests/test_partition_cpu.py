@@ -74,7 +74,7 @@ def _gather_worker(rank, world, port, q):
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     import torch.distributed as dist
     from types import SimpleNamespace
-    from dual_dmp_b200.partition import _AllGatherRows
+    from dual_dmp_b200.partition import PartitionedGraph, _AllGatherRows
     dist.init_process_group("gloo", rank=rank, world_size=world)
     n = 11
     perm = torch.from_numpy(np.random.RandomState(3).permutation(n))
@@ -82,6 +82,7 @@ def _gather_worker(rank, world, port, q):
     lo, hi = int(bounds[rank]), int(bounds[rank + 1])
     pg = SimpleNamespace(plan=SimpleNamespace(bounds=bounds), world=world, group=None, perm_all=perm,
                          own_ids=perm[lo:hi])
+    pg.all_gather_equal = lambda mine: PartitionedGraph.all_gather_equal(pg, mine)     # the product's transport
     full_ref = torch.arange(n * 3, dtype=torch.float32).view(n, 3)            # caller numbering
     own = full_ref[perm[lo:hi]].clone().requires_grad_(True)
     full = _AllGatherRows.apply(own, pg)
