@@ -14,9 +14,13 @@ namespace ddmp {
 constexpr int kFinCh = 8;
 constexpr int kFinLanes = 128;
 constexpr int kFinThreads = kFinCh * kFinLanes;
-template <int SETS>
+// MOMENTS (SETS == 2 only): the partials are per-block (sum_b, M2_b about the block mean) as the aggregation kernels
+// emit them; each block contributes (sum_b, M2_b + sum_b^2 / n_b) -- its sum of squares, rebuilt in float64 -- with
+// n_b = rows_per_block except for the last block.  Summed in float64, var = Q/n - (S/n)^2 then cancels in float64
+// instead of float32: relative error ~1e-7 * |mean|/sigma instead of ~1e-7 * (mean/sigma)^2.
+template <int SETS, bool MOMENTS = false>
 __device__ __forceinline__ void reduce_partials(const float* __restrict__ partials, int64_t nblk, int C, int c,
-                                                double (&out)[SETS]) {
+                                                double (&out)[SETS], int64_t n_rows = 0, int rows_per_block = 0) {
     __shared__ double red[kFinLanes][SETS][kFinCh + 1];
     const int tx = threadIdx.x % kFinCh, ty = threadIdx.x / kFinCh;
     double acc[SETS];
@@ -31,13 +35,27 @@ __device__ __forceinline__ void reduce_partials(const float* __restrict__ partia
 #pragma unroll
                 for (int s = 0; s < SETS; ++s) v[u][s] = __ldg(partials + ((b + u * kFinLanes) * SETS + s) * C + c);
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
+            for (int u = 0; u < 4; ++u) {
+                if (MOMENTS) {          // b + 3*kFinLanes < nblk: none of these four is the last block
+                    acc[0] += (double)v[u][0];
+                    acc[SETS - 1] += (double)v[u][SETS - 1] + (double)v[u][0] * (double)v[u][0] / (double)rows_per_block;
+                } else {
 #pragma unroll
-                for (int s = 0; s < SETS; ++s) acc[s] += (double)v[u][s];
+                    for (int s = 0; s < SETS; ++s) acc[s] += (double)v[u][s];
+                }
+            }
         }
         for (; b < nblk; b += kFinLanes) {
+            if (MOMENTS) {
+                const double nb = (b == nblk - 1) ? (double)(n_rows - (nblk - 1) * (int64_t)rows_per_block)
+                                                  : (double)rows_per_block;
+                const double sb = (double)__ldg(partials + (b * SETS) * C + c);
+                acc[0] += sb;
+                acc[SETS - 1] += (double)__ldg(partials + (b * SETS + SETS - 1) * C + c) + sb * sb / nb;
+            } else {
 #pragma unroll
-            for (int s = 0; s < SETS; ++s) acc[s] += (double)__ldg(partials + (b * SETS + s) * C + c);
+                for (int s = 0; s < SETS; ++s) acc[s] += (double)__ldg(partials + (b * SETS + s) * C + c);
+            }
         }
     }
 #pragma unroll
@@ -52,34 +70,62 @@ __device__ __forceinline__ void reduce_partials(const float* __restrict__ partia
     }
 }
 
+// per-channel batch statistics from S = sum y and Q = sum y^2 (float64)
+__device__ __forceinline__ void bn_stats_write(double S, double Q, int64_t n, int c, const float* gamma, const float* beta,
+                                               float eps, float momentum, float* running_mean, float* running_var,
+                                               float* mean, float* rstd, float* scale, float* shift, float* bound) {
+    const double m = S / (double)n;
+    double var = Q / (double)n - m * m;
+    if (var < 0.0) var = 0.0;
+    const float r = (float)(1.0 / sqrt(var + (double)eps));
+    const float mf = (float)m;
+    const float sc = gamma[c] * r;
+    mean[c] = mf;
+    rstd[c] = r;
+    scale[c] = sc;
+    shift[c] = beta[c] - mf * sc;
+    // no sample of a batch of n lies more than sqrt(n-1) (biased) standard deviations from the batch mean, so
+    // |scale*y + shift| <= |gamma|*sqrt(n-1) + |beta| for every row: the operand bound of the fp16-split GEMMs
+    if (bound) bound[c] = fabsf(gamma[c]) * sqrtf((float)(n > 1 ? n - 1 : 1)) + fabsf(beta[c]);
+    if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mf;
+    if (running_var) {
+        const double unbiased = (n > 1) ? var * ((double)n / (double)(n - 1)) : var;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+    }
+}
+
+// partials: [nblk][2][C] per-block (sum, M2 about the block mean) from the aggregation kernels' epilogue
 __global__ void __launch_bounds__(kFinThreads)
-bn_stats_finalize_kernel(const float* __restrict__ partials, int64_t nblk, int64_t n, int C,
+bn_stats_finalize_kernel(const float* __restrict__ partials, int64_t nblk, int64_t n, int C, int rows_per_block,
                          const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float momentum,
                          float* running_mean, float* running_var, float* mean, float* rstd, float* scale,
                          float* shift, float* bound) {
     const int c = blockIdx.x * kFinCh + (threadIdx.x % kFinCh);
     double s[2];
-    reduce_partials<2>(partials, nblk, C, c, s);
-    if (threadIdx.x < kFinCh && c < C) {
-        const double m = s[0] / (double)n;
-        double var = s[1] / (double)n - m * m;
-        if (var < 0.0) var = 0.0;
-        const float r = (float)(1.0 / sqrt(var + (double)eps));
-        const float mf = (float)m;
-        const float sc = gamma[c] * r;
-        mean[c] = mf;
-        rstd[c] = r;
-        scale[c] = sc;
-        shift[c] = beta[c] - mf * sc;
-        // no sample of a batch of n lies more than sqrt(n-1) (biased) standard deviations from the batch mean, so
-        // |scale*y + shift| <= |gamma|*sqrt(n-1) + |beta| for every row: the operand bound of the fp16-split GEMMs
-        if (bound) bound[c] = fabsf(gamma[c]) * sqrtf((float)(n > 1 ? n - 1 : 1)) + fabsf(beta[c]);
-        if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mf;
-        if (running_var) {
-            const double unbiased = (n > 1) ? var * ((double)n / (double)(n - 1)) : var;
-            running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
-        }
-    }
+    reduce_partials<2, true>(partials, nblk, C, c, s, n, rows_per_block);
+    if (threadIdx.x < kFinCh && c < C)
+        bn_stats_write(s[0], s[1], n, c, gamma, beta, eps, momentum, running_mean, running_var, mean, rstd, scale,
+                       shift, bound);
+}
+
+// the same reduction without the finalize: this rank's (sum y, sum y^2) in float64 (partitioned mode: all-reduced next)
+__global__ void __launch_bounds__(kFinThreads)
+bn_stats_rank_sums_kernel(const float* __restrict__ partials, int64_t nblk, int64_t n, int C, int rows_per_block,
+                          double* __restrict__ sums) {
+    const int c = blockIdx.x * kFinCh + (threadIdx.x % kFinCh);
+    double s[2];
+    reduce_partials<2, true>(partials, nblk, C, c, s, n, rows_per_block);
+    if (threadIdx.x < kFinCh && c < C) { sums[c] = s[0]; sums[C + c] = s[1]; }
+}
+
+__global__ void bn_stats_from_sums_kernel(const double* __restrict__ sums, int64_t n, int C,
+                                          const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                          float momentum, float* running_mean, float* running_var, float* mean,
+                                          float* rstd, float* scale, float* shift, float* bound) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < C)
+        bn_stats_write(sums[c], sums[C + c], n, c, gamma, beta, eps, momentum, running_mean, running_var, mean, rstd,
+                       scale, shift, bound);
 }
 
 __global__ void __launch_bounds__(kFinThreads)
@@ -217,9 +263,33 @@ int ddmp_bn_stats_finalize(const float* partials, int64_t nblk, int64_t n, int32
     using namespace ddmp;
     DDMP_REQUIRE(partials && gamma && beta && mean && rstd && scale && shift, "bn_stats_finalize: null pointer");
     DDMP_REQUIRE(n > 0 && C > 0 && nblk > 0, "bn_stats_finalize: bad shape");
+    const int rpb = ddmp_rows_per_block(C);
+    DDMP_REQUIRE(nblk == ceil_div(n, rpb), "bn_stats_finalize: %lld partial blocks do not cover %lld rows in blocks of %d",
+                 (long long)nblk, (long long)n, rpb);
     bn_stats_finalize_kernel<<<(unsigned)ceil_div(C, kFinCh), kFinThreads, 0, as_stream(stream)>>>(
-        partials, nblk, n, C, gamma, beta, eps, momentum, running_mean, running_var, mean, rstd, scale, shift, bound);
+        partials, nblk, n, C, rpb, gamma, beta, eps, momentum, running_mean, running_var, mean, rstd, scale, shift, bound);
     return check_launch("bn_stats_finalize");
+}
+
+int ddmp_bn_stats_rank_sums(const float* partials, int64_t nblk, int64_t n, int32_t C, double* sums, void* stream) {
+    using namespace ddmp;
+    DDMP_REQUIRE(partials && sums && n > 0 && C > 0 && nblk > 0, "bn_stats_rank_sums: bad arguments");
+    const int rpb = ddmp_rows_per_block(C);
+    DDMP_REQUIRE(nblk == ceil_div(n, rpb), "bn_stats_rank_sums: partial blocks do not cover the rows");
+    bn_stats_rank_sums_kernel<<<(unsigned)ceil_div(C, kFinCh), kFinThreads, 0, as_stream(stream)>>>(partials, nblk, n, C,
+                                                                                                  rpb, sums);
+    return check_launch("bn_stats_rank_sums");
+}
+
+int ddmp_bn_stats_finalize_sums(const double* sums, int64_t n, int32_t C, const float* gamma, const float* beta,
+                                float eps, float momentum, float* running_mean, float* running_var, float* mean,
+                                float* rstd, float* scale, float* shift, float* bound, void* stream) {
+    using namespace ddmp;
+    DDMP_REQUIRE(sums && gamma && beta && mean && rstd && scale && shift && n > 0 && C > 0,
+                 "bn_stats_finalize_sums: bad arguments");
+    bn_stats_from_sums_kernel<<<(unsigned)ceil_div(C, 128), 128, 0, as_stream(stream)>>>(
+        sums, n, C, gamma, beta, eps, momentum, running_mean, running_var, mean, rstd, scale, shift, bound);
+    return check_launch("bn_stats_finalize_sums");
 }
 
 int ddmp_bn_bwd_reduce(const float* gX, const float* Y, const float* mean, const float* rstd, const float* scale,

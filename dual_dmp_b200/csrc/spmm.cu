@@ -48,6 +48,7 @@ spmm_gcn_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, con
     const int64_t row0 = blk * rows_per_block;
     const int64_t row_end = (row0 + rows_per_block < n) ? (row0 + rows_per_block) : n;
     float amx = 0.f;                                 // max |Y| over this thread's outputs of the row block
+    float wcnt = 0.f;                                // rows this group has folded into its running statistics
     if (STATS) {
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
@@ -137,6 +138,8 @@ spmm_gcn_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, con
             if (kk < nend) { nmyc = __ldg(col + kk); nmyw = __ldg(w + kk); }
         }
         float* yp = Y + r * C;
+        wcnt += 1.f;
+        const float winv = 1.f / wcnt;
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
             float4 o = acc[v];
@@ -145,12 +148,14 @@ spmm_gcn_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, con
             }
             st4(yp + (v * G + lg) * 4, o);
             amx = fmaxf(fmaxf(amx, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
-            if (STATS) {
+            if (STATS) {                            // Welford: running mean and M2 of this group's rows (see bn.cu)
                 float4 s = *reinterpret_cast<float4*>(myred + (v * G + lg) * 4);
                 float4 q = *reinterpret_cast<float4*>(myred + C + (v * G + lg) * 4);
-                s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
-                q.x = fmaf(o.x, o.x, q.x); q.y = fmaf(o.y, o.y, q.y);
-                q.z = fmaf(o.z, o.z, q.z); q.w = fmaf(o.w, o.w, q.w);
+                float d;
+                d = o.x - s.x; s.x = fmaf(d, winv, s.x); q.x = fmaf(d, o.x - s.x, q.x);
+                d = o.y - s.y; s.y = fmaf(d, winv, s.y); q.y = fmaf(d, o.y - s.y, q.y);
+                d = o.z - s.z; s.z = fmaf(d, winv, s.z); q.z = fmaf(d, o.z - s.z, q.z);
+                d = o.w - s.w; s.w = fmaf(d, winv, s.w); q.w = fmaf(d, o.w - s.w, q.w);
                 st4(myred + (v * G + lg) * 4, s);
                 st4(myred + C + (v * G + lg) * 4, q);
             }
@@ -159,14 +164,26 @@ spmm_gcn_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, con
     }
 
     if (STATS) {
-        // combine the GROUPS row groups of this CTA channel-wise in a fixed order
+        // merge the GROUPS row groups of this CTA channel-wise in group order (Chan et al.): block (sum, M2 about its mean)
         __syncthreads();
         float* outp = partials + blk * 2 * C;
-        for (int i = threadIdx.x; i < 2 * C; i += 256) {
-            float t = 0.f;
-#pragma unroll 8
-            for (int g = 0; g < GROUPS; ++g) t += red[g * 2 * C + i];
-            outp[i] = t;
+        const int rows_blk = (int)(row_end - row0);
+        for (int ch = threadIdx.x; ch < C; ch += 256) {
+            float n_a = 0.f, mean = 0.f, m2 = 0.f;
+#pragma unroll 4
+            for (int g = 0; g < GROUPS; ++g) {
+                if (g < rows_blk) {
+                    const float n_b = (float)((rows_blk - g + GROUPS - 1) / GROUPS);
+                    const float mb = red[g * 2 * C + ch], qb = red[g * 2 * C + C + ch];
+                    const float n = n_a + n_b;
+                    const float d = mb - mean;
+                    mean = fmaf(d, n_b / n, mean);
+                    m2 += qb + d * d * (n_a * n_b / n);
+                    n_a = n;
+                }
+            }
+            outp[ch] = mean * n_a;
+            outp[C + ch] = m2;
         }
         __syncthreads();
     }

@@ -111,7 +111,8 @@ spmm_tile_kernel(const __grid_constant__ CUtensorMap hmap, const Args a) {
     }
     float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
     if (BIAS) bsum = ldg4(a.bias + ch0 + lg * 4);
-    float4 ssum = make_float4(0.f, 0.f, 0.f, 0.f), qsum = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 ssum = make_float4(0.f, 0.f, 0.f, 0.f), qsum = make_float4(0.f, 0.f, 0.f, 0.f);     // running mean, M2
+    float cnt = 0.f;
     float amx = 0.f;
     __syncthreads();
     mbar_wait(&bar, 0);
@@ -156,26 +157,41 @@ spmm_tile_kernel(const __grid_constant__ CUtensorMap hmap, const Args a) {
         if (BIAS) { acc.x += bsum.x; acc.y += bsum.y; acc.z += bsum.z; acc.w += bsum.w; }
         st4(a.Y + (row0 + r) * a.C + ch0 + lg * 4, acc);
         amx = fmaxf(fmaxf(amx, fmaxf(fabsf(acc.x), fabsf(acc.y))), fmaxf(fabsf(acc.z), fabsf(acc.w)));
-        if (STATS) {
-            ssum.x += acc.x; ssum.y += acc.y; ssum.z += acc.z; ssum.w += acc.w;
-            qsum.x = fmaf(acc.x, acc.x, qsum.x); qsum.y = fmaf(acc.y, acc.y, qsum.y);
-            qsum.z = fmaf(acc.z, acc.z, qsum.z); qsum.w = fmaf(acc.w, acc.w, qsum.w);
+        if (STATS) {                                // Welford: running mean and M2 of this thread's rows (see bn.cu)
+            cnt += 1.f;
+            const float inv = 1.f / cnt;
+            float d;
+            d = acc.x - ssum.x; ssum.x = fmaf(d, inv, ssum.x); qsum.x = fmaf(d, acc.x - ssum.x, qsum.x);
+            d = acc.y - ssum.y; ssum.y = fmaf(d, inv, ssum.y); qsum.y = fmaf(d, acc.y - ssum.y, qsum.y);
+            d = acc.z - ssum.z; ssum.z = fmaf(d, inv, ssum.z); qsum.z = fmaf(d, acc.z - ssum.z, qsum.z);
+            d = acc.w - ssum.w; ssum.w = fmaf(d, inv, ssum.w); qsum.w = fmaf(d, acc.w - ssum.w, qsum.w);
         }
     }
 
     if (STATS) {
-        // per-group sums -> shared memory (over the tile, which is dead now), then channel-wise in group order
+        // per-group (mean, M2) -> shared memory (over the tile, which is dead now); then one thread per channel merges the
+        // groups in group order (Chan et al.) and writes the block's (sum, M2 about the block mean)
         __syncthreads();
         st4(red + gid * 2 * CS + lg * 4, ssum);
         st4(red + gid * 2 * CS + CS + lg * 4, qsum);
         __syncthreads();
         float* outp = a.partials + blk * 2 * a.C;
-        for (int i = threadIdx.x; i < 2 * CS; i += kThreads) {
-            float t = 0.f;
-#pragma unroll 8
-            for (int g = 0; g < GROUPS; ++g) t += red[g * 2 * CS + i];
-            const int set = i / CS, ch = i % CS;
-            outp[set * a.C + ch0 + ch] = t;
+        for (int ch = threadIdx.x; ch < CS; ch += kThreads) {
+            float n_a = 0.f, mean = 0.f, m2 = 0.f;
+#pragma unroll 4
+            for (int g = 0; g < GROUPS; ++g) {
+                const float n_b = (float)((rows - g + GROUPS - 1) / GROUPS);      // rows g, g+GROUPS, ... of this block
+                if (g < rows) {
+                    const float mb = red[g * 2 * CS + ch], qb = red[g * 2 * CS + CS + ch];
+                    const float n = n_a + n_b;
+                    const float d = mb - mean;
+                    mean = fmaf(d, n_b / n, mean);
+                    m2 += qb + d * d * (n_a * n_b / n);
+                    n_a = n;
+                }
+            }
+            outp[ch0 + ch] = mean * n_a;
+            outp[a.C + ch0 + ch] = m2;
         }
     }
     if (a.amax) {

@@ -139,6 +139,24 @@ def bn_stats_finalize(partials, n, gamma, beta, running_mean=None, running_var=N
     return stats
 
 
+def bn_rank_sums(partials, n):
+    """partitioned mode: this rank's per-channel (sum y, sum y^2) in float64 [2, C] from the aggregation partials"""
+    nblk, _, C = partials.shape
+    sums = torch.empty(2, C, dtype=torch.float64, device=partials.device)
+    lib.call("ddmp_bn_stats_rank_sums", ptr(partials), nblk, n, C, ptr(sums), stream_ptr(partials.device))
+    return sums
+
+
+def bn_stats_finalize_sums(sums, n, gamma, beta, running_mean=None, running_var=None):
+    """batch statistics from (all-reduced) float64 sums [2, C] and the global row count"""
+    C = sums.shape[1]
+    stats = torch.empty(5, C, dtype=torch.float32, device=sums.device)
+    lib.call("ddmp_bn_stats_finalize_sums", ptr(sums), n, C, ptr(gamma), ptr(beta), BN_EPS, BN_MOMENTUM,
+             ptr(running_mean), ptr(running_var), ptr(stats[0]), ptr(stats[1]), ptr(stats[2]), ptr(stats[3]),
+             ptr(stats[4]), stream_ptr(sums.device))
+    return stats
+
+
 def act_bound(stats):
     """per-channel upper bound of |lrelu(scale*Y+shift)| (training-mode batch statistics only), else None"""
     return stats[4] if stats.shape[0] > 4 else None
@@ -295,8 +313,8 @@ class GcnNetFunction(torch.autograd.Function):
                 if comm is None:
                     st = bn_stats_finalize(partials, n, gammas[l], betas[l], rm, rv)
                 else:
-                    sums = comm.allreduce_(partials_to_sums(partials))
-                    st = bn_stats_finalize(sums.view(1, 2, cout), comm.n_global, gammas[l], betas[l], rm, rv)
+                    sums = comm.allreduce_(bn_rank_sums(partials, n))          # float64 (sum y, sum y^2)
+                    st = bn_stats_finalize_sums(sums, comm.n_global, gammas[l], betas[l], rm, rv)
             else:
                 Y = spmm_gcn(graph, H, bias=bs[l], n_rows=n)
                 rm, rv = bn_buffers[l]

@@ -103,8 +103,10 @@ int64_t ddmp_spmm_bn_bwd_tile_blocks(int64_t n, int32_t C);
 int64_t ddmp_spmm_bn_bwd_tile_amax_len(int64_t n, int32_t C);
 
 /* ---- BatchNorm1d (training mode) + LeakyReLU ------------------------------------------------------------ */
-/* partials [nblk][2][C] -> batch mean / biased var; rstd = 1/sqrt(var+eps); scale = gamma*rstd;
- * shift = beta - mean*scale; running stats updated in place when non-NULL (momentum, unbiased var).
+/* partials [nblk][2][C] = per row block (sum of y, M2 = sum of (y - block mean)^2), as ddmp_spmm_gcn's epilogue emits
+ * them (Welford per thread, Chan merge per block; nblk = ddmp_num_row_blocks(n, C)) -> batch mean / biased var, combined
+ * in float64 in block order; rstd = 1/sqrt(var+eps); scale = gamma*rstd; shift = beta - mean*scale; running stats
+ * updated in place when non-NULL (momentum, unbiased var).
  * The normalise + LeakyReLU itself is applied lazily by the consumer (GEMM / head prologue).
  * bound (optional, [C]): |gamma|*sqrt(n-1)+|beta| >= |scale*y+shift| for every row of the batch (the `amax` input
  * of the dense transforms).
@@ -112,6 +114,12 @@ int64_t ddmp_spmm_bn_bwd_tile_amax_len(int64_t n, int32_t C);
 int ddmp_bn_stats_finalize(const float* partials, int64_t nblk, int64_t n, int32_t C, const float* gamma,
                            const float* beta, float eps, float momentum, float* running_mean, float* running_var,
                            float* mean, float* rstd, float* scale, float* shift, float* bound, void* stream);
+/* Partitioned mode: this rank's (sum y, sum y^2) per channel in float64 [2][C] from the same partials (all-reduced over
+ * the ranks, then ddmp_bn_stats_finalize_sums with the global row count). */
+int ddmp_bn_stats_rank_sums(const float* partials, int64_t nblk, int64_t n, int32_t C, double* sums, void* stream);
+int ddmp_bn_stats_finalize_sums(const double* sums, int64_t n, int32_t C, const float* gamma, const float* beta,
+                                float eps, float momentum, float* running_mean, float* running_var, float* mean,
+                                float* rstd, float* scale, float* shift, float* bound, void* stream);
 /* Backward of LeakyReLU(BN(Y)) given gX = dL/d(activated output):  gZ = gX * lrelu'(scale*Y+shift),
  * xhat = (Y-mean)*rstd;  partials[b][0][c] = sum gZ, [b][1][c] = sum gZ*xhat. */
 int ddmp_bn_bwd_reduce(const float* gX, const float* Y, const float* mean, const float* rstd, const float* scale,

@@ -79,7 +79,10 @@ def run_oracle(case, k, bnfloop, iters, seed, threads, log):
             "seconds": time.perf_counter() - t0}
 
 
-def run_product(case, k, bnfloop, iters, seed, path, log):
+def run_product(case, k, bnfloop, iters, seed, path, log, perturb=0):
+    """``perturb`` > 0: every initial weight is multiplied by (1 + 1e-7 * N(0,1)) drawn with that seed -- a rounding-level
+    perturbation, like the reduction-order changes that distinguish the oracle's own runs; the chaotic fit turns it into
+    an independent trajectory, which gives the (otherwise bitwise deterministic) product an ensemble"""
     from dual_dmp_b200.step import DualStep
     from dual_dmp_b200.util import loss as L
     from dual_dmp_b200.util.datamaker import dataset_from_meshes
@@ -91,6 +94,12 @@ def run_product(case, k, bnfloop, iters, seed, path, log):
     posnet, normnet = PosNet(dev).to(dev), NormalNet(dev).to(dev)
     posnet.load_state_dict(pos_ref.state_dict())
     normnet.load_state_dict(nrm_ref.state_dict())
+    if perturb:
+        g = torch.Generator(device="cpu").manual_seed(1000 + int(perturb))
+        with torch.no_grad():
+            for net in (posnet, normnet):
+                for p_ in net.parameters():
+                    p_.mul_((1.0 + 1e-7 * torch.randn(p_.shape, generator=g)).to(dev))
     ds = dataset_from_meshes(n_mesh, s_mesh)
     curve, norm_curve, losses = [], [], []
     t0 = time.perf_counter()

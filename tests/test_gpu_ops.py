@@ -27,6 +27,11 @@ def graphs():
     return out
 
 
+def lib_rows_per_block(C):
+    from dual_dmp_b200._lib import lib
+    return int(lib.query("ddmp_rows_per_block", C))
+
+
 def _ref_aggregate(edge_index, n, H):
     from oracle.gcn_ref import gcn_norm_ref
     idx, w = gcn_norm_ref(edge_index, n, torch.float64)
@@ -71,9 +76,13 @@ def test_spmm_matches_oracle(graphs, C, which):
     Hd, bd = H.to(DEV), bias.to(DEV)
     if C in (32, 64, 128, 256, 512):
         Y, partials = F_.spmm_gcn(graph, Hd, bias=bd, stats=True)
-        s = partials.double().sum(dim=0).cpu()
-        assert rel_err(s[0], ref.sum(dim=0)) < 1e-5
-        assert rel_err(s[1], (ref * ref).sum(dim=0)) < 1e-5
+        # partials: per row block (sum, M2 about the block mean); sum of squares = sum_b (M2_b + sum_b^2 / n_b)
+        pb = partials.double().cpu()
+        rpb = lib_rows_per_block(C)
+        n_b = torch.full((pb.shape[0], 1), float(rpb), dtype=torch.float64)
+        n_b[-1] = graph.n - (pb.shape[0] - 1) * rpb
+        assert rel_err(pb[:, 0].sum(dim=0), ref.sum(dim=0)) < 1e-5
+        assert rel_err((pb[:, 1] + pb[:, 0] ** 2 / n_b).sum(dim=0), (ref * ref).sum(dim=0)) < 1e-5
         Y2, partials2 = F_.spmm_gcn(graph, Hd, bias=bd, stats=True)
         assert torch.equal(Y, Y2) and torch.equal(partials, partials2)          # deterministic
         Y3 = F_.spmm_gcn(graph, Hd)
@@ -169,6 +178,40 @@ def test_batchnorm_lrelu_forward_backward(C, n):
     assert e_f < 2e-5 and max(e_b) < 5e-5, (e_f, e_b)
     assert dbias.abs().max() < 1e-3 * dY.abs().sum(dim=0).max()          # true gradient of a pre-BN bias is 0
     assert rel_err(F_.colsum(Y), Y0.double().sum(dim=0)) < 1e-5
+
+
+@pytest.mark.parametrize("ratio", [0.0, 100.0, 1000.0, 1.0e4])
+@pytest.mark.parametrize("C,n", [(32, 70001), (256, 33333), (512, 1001)])
+def test_batchnorm_statistics_with_large_mean_over_sigma(C, n, ratio):
+    """the variance must not be formed as E[y^2] - E[y]^2 in float32 (SURVEY.md §7 hard part 3): the aggregation epilogue
+    emits per-block (sum, M2 about the block mean) (Welford per thread, Chan merge per block) and the finalize combines
+    them in float64, so the relative error of var / rstd grows like |mean|/sigma * 1e-7, not (mean/sigma)^2 * 1e-7.
+    Also the partitioned-mode route (rank sums in float64 -> finalize_sums) and the tile-staged / gather kernels"""
+    from dual_dmp_b200 import functional as F_
+    from dual_dmp_b200._lib import lib
+    from dual_dmp_b200.graph import GcnGraph
+    torch.manual_seed(C)
+    sigma = torch.rand(C) * 2 + 0.5
+    Y0 = torch.randn(n, C) * sigma + ratio * sigma * torch.where(torch.rand(C) < 0.5, -1.0, 1.0)
+    graph = GcnGraph(torch.zeros(2, 0, dtype=torch.long), n, DEV, reorder=False)           # A_hat = I
+    Yd = Y0.to(DEV)
+    ref_mean = Yd.double().mean(0)
+    ref_var = Yd.double().var(0, unbiased=False)
+    gamma, beta = torch.ones(C, device=DEV), torch.zeros(C, device=DEV)
+    tol = 2e-6 + 4e-7 * ratio
+    try:
+        for mode in (2, 0):
+            lib.query("ddmp_spmm_use_tile_kernel", mode)
+            _, partials = F_.spmm_gcn(graph, Yd, stats=True)
+            st = F_.bn_stats_finalize(partials, n, gamma, beta)
+            e_mean = float((st[0].double() - ref_mean).abs().max() / ref_mean.abs().max().clamp_min(1.0))
+            e_rstd = rel_err(st[1], torch.rsqrt(ref_var + 1e-5))
+            st2 = F_.bn_stats_finalize_sums(F_.bn_rank_sums(partials, n), n, gamma, beta)
+            report(f"bn stats |mean|/sigma={ratio:g} C={C} n={n} kernel mode {mode}", (e_mean, e_rstd))
+            assert e_mean < 2e-7 and e_rstd < tol, (mode, e_mean, e_rstd, tol)
+            assert torch.equal(st, st2)
+    finally:
+        lib.query("ddmp_spmm_use_tile_kernel", 1)
 
 
 @pytest.mark.parametrize("kind", [0, 1])
