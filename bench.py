@@ -768,6 +768,7 @@ def run_partitioned(args, weak):
         pt.patch(PartitionedGraph, "allreduce_", "all_reduce: BatchNorm sums + weight gradients (NCCL)")
         pt.patch(PartitionedGraph, "gather_outputs", "all_gather of the network outputs")
     pt.patch(F_, "spmm_gcn", "SpMM")
+    pt.patch(F_, "bn_stats_finalize_peer", "BatchNorm statistics: reduce + all-reduce over NVLink peer memory + finalize (one kernel)")
     for nm in ("gemm_xw", "gemm_dx", "gemm_dw"):
         pt.patch(F_, nm, "dense transforms")
     pt.patch(L, "dual_loss", "losses forward + backward (dual_loss_kernel, replicated over the whole mesh)")
@@ -824,10 +825,14 @@ def run_partitioned(args, weak):
                        "memory, runs DualStep.step over the PartitionedNets, reads the loss back (.item())"}
 
     halo = {}
+    peer_errors, peer_used = 0, False
     if world > 1:
         for name, net in (("vertex_graph", posnet), ("face_graph", normnet)):
             g = net.last_graph
             halo[name] = {"owned_rows": g.n, "halo_rows": g.n_halo, "sent_rows": g.n_send}
+            if g.peer is not None:
+                peer_used = True
+                peer_errors += g.peer.error()
     mem = torch.cuda.max_memory_allocated(dev) / 2 ** 30
 
     # ---- side measurement: mode A (one independent 1M-face fit per GPU, no data-path collective) ---------------------
@@ -870,6 +875,9 @@ def run_partitioned(args, weak):
                           "iters_per_s_of_this_mesh": 1000.0 / ms_per_step, "rank0_partition": halo,
                           "rank0_peak_mem_GiB": round(mem, 2), "setup_s": round(setup_s, 1),
                           "l2_policy": "working set (>=10 GB of saved activations per rank) exceeds L2",
+                          "batchnorm_allreduce": ("fused into the statistics / backward-sum kernels: one-shot exchange over NVLink "
+                                                  "peer memory (csrc/comm.cu), %d bounded-wait errors" % peer_errors)
+                                                 if peer_used else "NCCL all_reduce",
                           "streams": "PosNet / NormalNet on two compute streams, one NCCL communicator each" if overlap
                                      else "one compute stream",
                           "phases_ms_per_step_rank0": {k_: round(v, 3) for k_, v in sorted(phases.items())},

@@ -118,6 +118,20 @@ bn_stats_rank_sums_kernel(const float* __restrict__ partials, int64_t nblk, int6
     if (threadIdx.x < kFinCh && c < C) { sums[c] = s[0]; sums[C + c] = s[1]; }
 }
 
+// eval mode: the same [mean, rstd, scale, shift] table from the running statistics (reference: nn.BatchNorm1d.eval())
+__global__ void bn_eval_stats_kernel(const float* __restrict__ running_mean, const float* __restrict__ running_var,
+                                     const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int C,
+                                     float* mean, float* rstd, float* scale, float* shift) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float r = 1.0f / sqrtf(running_var[c] + eps);
+    const float sc = gamma[c] * r;
+    mean[c] = running_mean[c];
+    rstd[c] = r;
+    scale[c] = sc;
+    shift[c] = beta[c] - running_mean[c] * sc;
+}
+
 __global__ void bn_stats_from_sums_kernel(const double* __restrict__ sums, int64_t n, int C,
                                           const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                           float momentum, float* running_mean, float* running_var, float* mean,
@@ -290,6 +304,16 @@ int ddmp_bn_stats_finalize_sums(const double* sums, int64_t n, int32_t C, const 
     bn_stats_from_sums_kernel<<<(unsigned)ceil_div(C, 128), 128, 0, as_stream(stream)>>>(
         sums, n, C, gamma, beta, eps, momentum, running_mean, running_var, mean, rstd, scale, shift, bound);
     return check_launch("bn_stats_finalize_sums");
+}
+
+int ddmp_bn_eval_stats(const float* running_mean, const float* running_var, const float* gamma, const float* beta,
+                       float eps, int32_t C, float* mean, float* rstd, float* scale, float* shift, void* stream) {
+    using namespace ddmp;
+    DDMP_REQUIRE(running_mean && running_var && gamma && beta && mean && rstd && scale && shift && C > 0,
+                 "bn_eval_stats: bad arguments");
+    bn_eval_stats_kernel<<<(unsigned)ceil_div(C, 128), 128, 0, as_stream(stream)>>>(running_mean, running_var, gamma, beta,
+                                                                                  eps, C, mean, rstd, scale, shift);
+    return check_launch("bn_eval_stats");
 }
 
 int ddmp_bn_bwd_reduce(const float* gX, const float* Y, const float* mean, const float* rstd, const float* scale,

@@ -157,6 +157,18 @@ def bn_stats_finalize_sums(sums, n, gamma, beta, running_mean=None, running_var=
     return stats
 
 
+def bn_stats_finalize_peer(partials, n_local, comm, gamma, beta, running_mean=None, running_var=None):
+    """partitioned mode: rank reduction + one-shot all-reduce over NVLink peer memory + BatchNorm table, one kernel"""
+    nblk, _, C = partials.shape
+    stats = torch.empty(5, C, dtype=torch.float32, device=partials.device)
+    peer = comm.peer
+    lib.call("ddmp_bn_stats_finalize_peer", ptr(partials), nblk, n_local, C, peer.ptrs, peer.rank, peer.world,
+             peer.next_seq(), comm.n_global, ptr(gamma), ptr(beta), BN_EPS, BN_MOMENTUM, ptr(running_mean),
+             ptr(running_var), ptr(stats[0]), ptr(stats[1]), ptr(stats[2]), ptr(stats[3]), ptr(stats[4]),
+             stream_ptr(partials.device))
+    return stats
+
+
 def act_bound(stats):
     """per-channel upper bound of |lrelu(scale*Y+shift)| (training-mode batch statistics only), else None"""
     return stats[4] if stats.shape[0] > 4 else None
@@ -178,6 +190,10 @@ def bn_lrelu_backward(gX, Y, stats, dY_out=None, comm=None):
     if comm is None:
         lib.call("ddmp_bn_bwd_finalize", ptr(partials), nblk, n, C, ptr(small[0]), ptr(small[1]), ptr(small[2]),
                  ptr(small[3]), st)
+    elif getattr(comm, "peer", None) is not None:
+        peer = comm.peer
+        lib.call("ddmp_bn_bwd_finalize_peer", ptr(partials), nblk, C, peer.ptrs, peer.rank, peer.world, peer.next_seq(),
+                 comm.n_global, ptr(small[0]), ptr(small[1]), ptr(small[2]), ptr(small[3]), st)
     else:
         sums = comm.allreduce_(partials_to_sums(partials))
         lib.call("ddmp_bn_bwd_finalize", ptr(sums), 1, comm.n_global, C, ptr(small[0]), ptr(small[1]), ptr(small[2]),
@@ -312,15 +328,17 @@ class GcnNetFunction(torch.autograd.Function):
                 rm, rv = bn_buffers[l]
                 if comm is None:
                     st = bn_stats_finalize(partials, n, gammas[l], betas[l], rm, rv)
+                elif getattr(comm, "peer", None) is not None:
+                    st = bn_stats_finalize_peer(partials, n, comm, gammas[l], betas[l], rm, rv)
                 else:
                     sums = comm.allreduce_(bn_rank_sums(partials, n))          # float64 (sum y, sum y^2)
                     st = bn_stats_finalize_sums(sums, comm.n_global, gammas[l], betas[l], rm, rv)
             else:
                 Y = spmm_gcn(graph, H, bias=bs[l], n_rows=n)
                 rm, rv = bn_buffers[l]
-                rstd = torch.rsqrt(rv + BN_EPS)
-                scale = gammas[l] * rstd
-                st = torch.stack([rm, rstd, scale, betas[l] - rm * scale])
+                st = torch.empty(4, cout, dtype=torch.float32, device=dev)      # mean, rstd, scale, shift (no bound)
+                lib.call("ddmp_bn_eval_stats", ptr(rm), ptr(rv), ptr(gammas[l]), ptr(betas[l]), BN_EPS, cout, ptr(st[0]),
+                         ptr(st[1]), ptr(st[2]), ptr(st[3]), stream_ptr(dev))
             Ys.append(Y)
             stats.append(st)
             if taps is not None:

@@ -91,6 +91,57 @@ class PartitionPlan:
                     send_counts=send_counts, recv_counts=recv_counts)
 
 
+class PeerComm:
+    """One exchange buffer per rank, mapped by every peer of the box through CUDA IPC: the transport of the fused
+    "reduce + all-reduce + finalize" BatchNorm kernels (csrc/comm.cu; ddmp_bn_stats_finalize_peer /
+    ddmp_bn_bwd_finalize_peer), which replace an NCCL all-reduce between two small kernels by one kernel that exchanges its
+    2*C sums with P2P stores over NVLink.  One instance per partitioned network (PosNet and NormalNet run on two streams:
+    each needs its own buffer and sequence counter).  ``DDMP_PEER_ALLREDUCE=0`` keeps the NCCL route."""
+
+    def __init__(self, rank: int, world: int, device, group=None):
+        import ctypes
+        self.rank, self.world, self.device = int(rank), int(world), torch.device(device)
+        self.seq = 0
+        set_device(self.device)
+        local = ctypes.c_void_p()
+        lib.call("ddmp_comm_alloc", ctypes.byref(local))
+        self.local = local.value
+        handle = ctypes.create_string_buffer(64)
+        lib.call("ddmp_comm_ipc_handle", self.local, handle)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle.raw), group=group)
+        self._opened = []
+        ptrs = (ctypes.c_void_p * self.world)()
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                ptrs[r] = self.local
+            else:
+                out = ctypes.c_void_p()
+                lib.call("ddmp_comm_ipc_open", ctypes.create_string_buffer(h, 64), ctypes.byref(out))
+                self._opened.append(out.value)
+                ptrs[r] = out.value
+        self.ptrs = ptrs
+        dist.barrier(group=group)                  # every rank has mapped every buffer before the first exchange
+
+    def next_seq(self) -> int:
+        self.seq += 1
+        return self.seq
+
+    def error(self) -> int:
+        import ctypes
+        e = ctypes.c_int32(0)
+        lib.call("ddmp_comm_error", self.local, ctypes.byref(e))
+        return int(e.value)
+
+    def close(self):
+        for p_ in self._opened:
+            lib.call("ddmp_comm_ipc_close", p_)
+        self._opened = []
+        if self.local:
+            lib.call("ddmp_comm_free", self.local)
+            self.local = None
+
+
 class PartitionedGraph:
     """Device-resident part of rank ``rank``; duck-types the GcnGraph fields the SpMM wrapper reads."""
 
@@ -117,6 +168,7 @@ class PartitionedGraph:
         self.own_ids = torch.from_numpy(plan.perm[self.lo:self.hi].copy()).to(dev)
         self.perm_all = torch.from_numpy(plan.perm.copy()).to(dev)
         self._send_bufs: dict = {}                           # width -> persistent packed-rows buffer
+        self.peer = None                                     # PeerComm (NVLink peer-memory BatchNorm reductions) or None
 
     # ---- collectives (NCCL on GPUs; enqueued on the current stream, no host synchronisation) -----------------------
     def exchange(self, X_ext: torch.Tensor) -> None:
@@ -204,6 +256,10 @@ class PartitionedNet(torch.nn.Module):
         coords = data.x_pos if is_pos else data.z2.detach()[:, :3]
         plan = PartitionPlan(edge_index, feats.shape[0], coords, self.world)
         pg = PartitionedGraph(plan, self.rank, dev, self.group)
+        import os
+        if self.world > 1 and dev.type == "cuda" and os.environ.get("DDMP_PEER_ALLREDUCE", "1") != "0" \
+                and dist.get_backend(self.group) == "nccl":
+            pg.peer = PeerComm(self.rank, self.world, dev, self.group)
         ids = pg.own_ids.cpu()
         x_own = feats.detach().cpu()[ids].contiguous().to(dev)                   # static inputs: sliced once
         xpos_own = data.x_pos.detach().cpu()[ids].contiguous().to(dev) if is_pos else None

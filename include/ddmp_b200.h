@@ -114,6 +114,9 @@ int64_t ddmp_spmm_bn_bwd_tile_amax_len(int64_t n, int32_t C);
 int ddmp_bn_stats_finalize(const float* partials, int64_t nblk, int64_t n, int32_t C, const float* gamma,
                            const float* beta, float eps, float momentum, float* running_mean, float* running_var,
                            float* mean, float* rstd, float* scale, float* shift, float* bound, void* stream);
+/* eval mode: the [mean, rstd, scale, shift] table from the running statistics. [ref: nn.BatchNorm1d.eval()] */
+int ddmp_bn_eval_stats(const float* running_mean, const float* running_var, const float* gamma, const float* beta,
+                       float eps, int32_t C, float* mean, float* rstd, float* scale, float* shift, void* stream);
 /* Partitioned mode: this rank's (sum y, sum y^2) per channel in float64 [2][C] from the same partials (all-reduced over
  * the ranks, then ddmp_bn_stats_finalize_sums with the global row count). */
 int ddmp_bn_stats_rank_sums(const float* partials, int64_t nblk, int64_t n, int32_t C, double* sums, void* stream);
@@ -236,6 +239,33 @@ int ddmp_face_normals_fwd(const float* pos, const int32_t* faces, float* fn, int
 int ddmp_face_normals_bwd(const float* pos, const int32_t* faces, const int32_t* corner_ptr,
                           const int32_t* corner_slot, const float* gfn, float* face_tmp, float* gpos, int64_t V,
                           int64_t F, void* stream);
+/* ---- partitioned mode: BatchNorm reductions over NVLink peer memory (csrc/comm.cu) ------------------------- */
+/* Every rank owns one exchange buffer (ddmp_comm_buffer_bytes() bytes, allocated and zeroed by ddmp_comm_alloc) that all
+ * peers of the box map through CUDA IPC (ddmp_comm_ipc_handle on the owner -> 64 opaque bytes -> ddmp_comm_ipc_open on
+ * each peer).  peer_buffers is a HOST array of `world` device pointers, entry r = rank r's buffer as mapped in this
+ * process (own entry = the local pointer).  seq = 1, 2, 3, ... must advance by one per call, identically on all ranks.
+ * ddmp_bn_stats_finalize_peer = this rank's float64 reduction of the aggregation partials + one-shot all-reduce through
+ * the peers' buffers (P2P stores, sequence flags, sum in rank order: bit-identical on every rank) + the BatchNorm table
+ * for the GLOBAL batch of n_global rows, in ONE kernel; replaces ddmp_bn_stats_rank_sums + an NCCL all-reduce +
+ * ddmp_bn_stats_finalize_sums.  ddmp_bn_bwd_finalize_peer does the same for the two BatchNorm-backward sums
+ * (partials [nblk][2][C] of ddmp_bn_bwd_reduce).  Waits are bounded; ddmp_comm_error reports a peer that never arrived.
+ * [ref: nn.BatchNorm1d over the whole batch, util/networks.py:31-42,51-62; no counterpart in the reference (single GPU)] */
+int64_t ddmp_comm_buffer_bytes(void);
+int ddmp_comm_alloc(void** out);
+int ddmp_comm_free(void* p);
+int ddmp_comm_ipc_handle(void* p, void* handle64);
+int ddmp_comm_ipc_open(const void* handle64, void** out);
+int ddmp_comm_ipc_close(void* p);
+int ddmp_comm_error(const void* p, int32_t* out);
+int ddmp_bn_stats_finalize_peer(const float* partials, int64_t nblk, int64_t n_local, int32_t C,
+                                const void* const* peer_buffers, int32_t rank, int32_t world, int64_t seq,
+                                int64_t n_global, const float* gamma, const float* beta, float eps, float momentum,
+                                float* running_mean, float* running_var, float* mean, float* rstd, float* scale,
+                                float* shift, float* bound, void* stream);
+int ddmp_bn_bwd_finalize_peer(const float* partials, int64_t nblk, int32_t C, const void* const* peer_buffers,
+                              int32_t rank, int32_t world, int64_t seq, int64_t n_global, float* dgamma, float* dbeta,
+                              float* c1, float* c2, void* stream);
+
 /* ---- mesh preprocessing on the device, float64 ------------------------------------------ */
 /* Conventions of the reference's offline tools, which need pymeshlab: uniform Laplacian smoothing x30 for the *_smooth
  * mesh, Gaussian noise along the vertex normal, unit-box normalisation, rescale to mean edge length 1.

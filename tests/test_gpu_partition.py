@@ -1,6 +1,7 @@
 """Partitioned mode on real GPUs (needs >= 2 devices; run with `gpurun --gpus 2 -- python -m pytest
-tests/test_gpu_partition.py -m gpu`): one mesh split over 2 ranks with NCCL halo exchange + BatchNorm / weight
-gradient all-reduce must reproduce the single-GPU result (outputs, losses, every parameter gradient)."""
+tests/test_gpu_partition.py -m gpu`): one mesh split over 2 ranks with NCCL halo exchange, the BatchNorm reductions
+fused with a one-shot all-reduce over NVLink peer memory (csrc/comm.cu) and the NCCL weight-gradient all-reduce must
+reproduce the single-GPU result (outputs, losses, every parameter gradient); replicas stay bit-identical."""
 import os
 import socket
 
@@ -82,7 +83,8 @@ def _worker(rank, world, port, q):
             flat = torch.cat([g2[k].reshape(-1) for k in sorted(g2)])
             ref0 = flat.clone()
             dist.broadcast(ref0, src=0)
-            res[f"{kind}{n}"] = dict(pos=rel_err(pos2, pos1), nrm=rel_err(nrm2, nrm1),
+            peer_ok = all(net.last_graph.peer is not None and net.last_graph.peer.error() == 0 for net in (posnet, normnet))
+            res[f"{kind}{n}"] = dict(pos=rel_err(pos2, pos1), nrm=rel_err(nrm2, nrm1), peer_allreduce=peer_ok,
                                      loss=max(abs(a - b) / abs(b) for a, b in zip(l2, l1)), grad=worst,
                                      flips=int(fl.item()), replicas_identical=bool(torch.equal(flat, ref0)))
             posnet.taps = normnet.taps = None
@@ -111,6 +113,7 @@ def test_partitioned_matches_single_gpu():
         report(f"partitioned rank {rank}", res)
         for case, r in res.items():
             assert r["pos"] < 2e-5 and r["nrm"] < 2e-5 and r["loss"] < 1e-5 and r["replicas_identical"], (rank, case, r)
+            assert r["peer_allreduce"], (rank, case, "BatchNorm reductions did not run over NVLink peer memory", r)
             # a LeakyReLU pre-activation within rounding of zero may take the other branch when the BatchNorm sums
             # are combined in a different order (tests/helpers.MaskedLeaky explains the effect); without such a flip
             # the gradients must agree to rounding
