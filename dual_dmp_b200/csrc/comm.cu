@@ -4,10 +4,11 @@
 // BatchNorm-backward sums of every layer; reference: nn.BatchNorm1d at util/networks.py:31-42,51-62 sees the whole
 // batch).  As NCCL calls they cost ~80 us each on 8 GPUs (latency, not bandwidth: 8 KB messages) between a reduction
 // kernel and a finalize kernel.  Here every rank owns a small exchange buffer that all peers map (CUDA IPC); the kernel
-//   1. reduces this rank's row-block partials in float64 (same fixed-order reduction as bn.cu),
-//   2. stores its 2*C sums into slot [parity][rank] of EVERY peer's buffer (P2P stores through NVSwitch),
-//   3. the last CTA to finish publishes a sequence number to every peer (release, system scope), waits until the
-//      sequence numbers of all peers have arrived in its own buffer (acquire), and
+//   1. reduces this rank's row-block partials in float64, (channels / 8) x (up to 16 row-block chunks) CTAs, fixed order;
+//   2. the last CTA to finish combines the chunks in order and stores the rank's 2*C sums into slot [parity][rank] of
+//      EVERY peer's buffer (P2P stores through NVSwitch),
+//   3. publishes a sequence number to every peer (release, system scope), waits until the sequence numbers of all peers
+//      have arrived in its own buffer (acquire), and
 //   4. sums the slots in RANK order -- every rank forms bit-identical totals -- and writes the BatchNorm table.
 // One-shot, latency-bound by a single NVLink round trip; slots are double-buffered by the parity of the sequence number
 // (a rank can be at most one exchange ahead of its slowest peer, because it cannot finish exchange s+1 before every peer
@@ -25,8 +26,11 @@ constexpr int kFinLanes = 128;
 constexpr int kFinThreads = kFinCh * kFinLanes;
 constexpr unsigned long long kSpinLimit = 1ull << 24;   // ~10 s of polling: ranks are at most one layer apart
 
+constexpr int kMaxSplit = 16;                 // CTAs along the row-block axis of the local reduction
+
 struct Buffer {                               // lives in device memory of its owner, mapped by every peer
     double slots[2][kMaxRanks][kMaxLen];
+    double local[kMaxSplit][kMaxLen];         // local: this rank's per-chunk sums, combined by the last CTA
     unsigned long long flags[2][kMaxRanks];   // sequence number last published by each rank, per parity
     unsigned int ticket;                      // local: CTAs of the running kernel that have finished
     unsigned int error;                       // local: set when a wait ran into kSpinLimit
@@ -54,12 +58,12 @@ __device__ __forceinline__ double ld_volatile_f64(const double* p) {
 // MOMENTS: partials are (sum_b, M2_b): set 1 contributes M2_b + sum_b^2 / n_b (see bn.cu reduce_partials)
 template <bool MOMENTS>
 __device__ __forceinline__ void reduce2(const float* __restrict__ partials, int64_t nblk, int C, int c, double (&out)[2],
-                                        int64_t n_rows, int rpb) {
+                                        int64_t n_rows, int rpb, int64_t b_begin, int64_t b_end) {
     __shared__ double red[kFinLanes][2][kFinCh + 1];
     const int tx = threadIdx.x % kFinCh, ty = threadIdx.x / kFinCh;
     double a0 = 0.0, a1 = 0.0;
     if (c < C) {
-        for (int64_t b = ty; b < nblk; b += kFinLanes) {
+        for (int64_t b = b_begin + ty; b < b_end; b += kFinLanes) {
             const double s0 = (double)__ldg(partials + (b * 2) * C + c);
             const double s1 = (double)__ldg(partials + (b * 2 + 1) * C + c);
             if (MOMENTS) {
@@ -97,26 +101,35 @@ bn_allreduce_kernel(const float* __restrict__ partials, int64_t nblk, int64_t n_
     Buffer* mine = peers.buf[rank];
     const int parity = (int)(seq & 1ull);
     const int c = blockIdx.x * kFinCh + (threadIdx.x % kFinCh);
+    // stage 1: the row blocks are cut into gridDim.y chunks; every CTA reduces (8 channels) x (one chunk) in float64
+    const int64_t chunk = (nblk + gridDim.y - 1) / gridDim.y;
+    const int64_t b0 = (int64_t)blockIdx.y * chunk;
+    const int64_t b1 = (b0 + chunk < nblk) ? (b0 + chunk) : nblk;
     double s[2];
-    reduce2<MODE == 0>(partials, nblk, C, c, s, n_local, rpb);
+    reduce2<MODE == 0>(partials, nblk, C, c, s, n_local, rpb, b0, b1);
     if (threadIdx.x < kFinCh && c < C) {
-        for (int p = 0; p < world; ++p) {                      // P2P stores into every rank's buffer (own one included)
-            peers.buf[p]->slots[parity][rank][c] = s[0];
-            peers.buf[p]->slots[parity][rank][C + c] = s[1];
-        }
+        mine->local[blockIdx.y][c] = s[0];
+        mine->local[blockIdx.y][C + c] = s[1];
     }
-    // last CTA of this rank: publish, wait for the peers, total, finalize
+    // last CTA of this rank: combine the chunks in order, publish to every peer, wait for the peers, total, finalize
     __shared__ bool is_last;
-    __threadfence_system();
+    __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
         const unsigned int t = atomicAdd(&mine->ticket, 1u);
-        is_last = (t == gridDim.x - 1);
+        is_last = (t == gridDim.x * gridDim.y - 1);
         if (is_last) mine->ticket = 0u;
     }
     __syncthreads();
     if (!is_last) return;
+    __threadfence();
+    for (int i = threadIdx.x; i < 2 * C; i += kFinThreads) {
+        double t = 0.0;
+        for (unsigned y = 0; y < gridDim.y; ++y) t += ld_volatile_f64(&mine->local[y][i]);
+        for (int p = 0; p < world; ++p) peers.buf[p]->slots[parity][rank][i] = t;      // P2P stores (own buffer included)
+    }
     __threadfence_system();
+    __syncthreads();
     if (threadIdx.x < world) st_release_sys(&peers.buf[threadIdx.x]->flags[parity][rank], seq);
     if (threadIdx.x < world) {
         unsigned long long spins = 0;
@@ -156,6 +169,13 @@ bn_allreduce_kernel(const float* __restrict__ partials, int64_t nblk, int64_t n_
             bo.c2[ch] = (float)(Q / (double)n_global);
         }
     }
+}
+
+// (channels / 8) x (row-block chunks): >= 512 blocks per CTA, at most kMaxSplit chunks
+static dim3 grid_for(int C, int64_t nblk) {
+    int64_t split = nblk / 512;
+    split = split < 1 ? 1 : (split > kMaxSplit ? kMaxSplit : split);
+    return dim3((unsigned)ceil_div(C, kFinCh), (unsigned)split);
 }
 
 static int fill_peers(Peers& p, const void* const* peer_ptrs, int world) {
@@ -240,7 +260,7 @@ int ddmp_bn_stats_finalize_peer(const float* partials, int64_t nblk, int64_t n_l
     if (rc != DDMP_OK) return rc;
     comm::StatsOut so{gamma, beta, eps, momentum, running_mean, running_var, mean, rstd, scale, shift, bound};
     comm::BwdOut bo{};
-    comm::bn_allreduce_kernel<0><<<(unsigned)ceil_div(C, comm::kFinCh), comm::kFinThreads, 0, as_stream(stream)>>>(
+    comm::bn_allreduce_kernel<0><<<comm::grid_for(C, nblk), comm::kFinThreads, 0, as_stream(stream)>>>(
         partials, nblk, n_local, C, rpb, peers, rank, world, (unsigned long long)seq, n_global, so, bo);
     return check_launch("bn_stats_finalize_peer");
 }
@@ -257,7 +277,7 @@ int ddmp_bn_bwd_finalize_peer(const float* partials, int64_t nblk, int32_t C, co
     if (rc != DDMP_OK) return rc;
     comm::StatsOut so{};
     comm::BwdOut bo{dgamma, dbeta, c1, c2};
-    comm::bn_allreduce_kernel<1><<<(unsigned)ceil_div(C, comm::kFinCh), comm::kFinThreads, 0, as_stream(stream)>>>(
+    comm::bn_allreduce_kernel<1><<<comm::grid_for(C, nblk), comm::kFinThreads, 0, as_stream(stream)>>>(
         partials, nblk, 0, C, 1, peers, rank, world, (unsigned long long)seq, n_global, so, bo);
     return check_launch("bn_bwd_finalize_peer");
 }
