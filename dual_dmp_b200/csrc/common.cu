@@ -4,9 +4,54 @@
 #include <atomic>
 #include <string.h>
 
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace ddmp {
+
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeFn encode_fn() {
+    static EncodeFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeFn>(p);
+    }();
+    return fn;
+}
+
+int make_tensor_map_2d(void* map, const float* base, int64_t outer, int64_t inner, int box_outer, int box_inner,
+                       bool swizzle128, const char* who) {
+    // the driver call needs a current context on THIS thread: the autograd engine's thread may reach its first kernel of
+    // a backward pass before any runtime call has bound the primary context to it
+    static thread_local const bool bound = (cudaFree(nullptr), true);
+    (void)bound;
+    EncodeFn enc = encode_fn();
+    if (!enc) {
+        set_error("%s: cuTensorMapEncodeTiled is not available from this driver", who);
+        return DDMP_ERR_CUDA;
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+    const cuuint64_t strides[1] = {(cuuint64_t)inner * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult rc = enc(reinterpret_cast<CUtensorMap*>(map), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base),
+                      dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) {
+        set_error("%s: cuTensorMapEncodeTiled failed (CUresult %d) for base=%p [%lld x %lld] box=%dx%d", who, (int)rc,
+                  (const void*)base, (long long)outer, (long long)inner, box_outer, box_inner);
+        return DDMP_ERR_CUDA;
+    }
+    return DDMP_OK;
+}
 
 static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};

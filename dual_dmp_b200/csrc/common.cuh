@@ -99,9 +99,17 @@ struct PerDeviceOnce {
     void mark() { done.fetch_or(bit(), std::memory_order_release); }
 };
 
+// 2-D tensor map (TMA descriptor) of a row-major fp32 [outer, inner] tensor, box = [box_outer, box_inner]; swizzle128:
+// CU_TENSOR_MAP_SWIZZLE_128B (box_inner * 4 must be 128 bytes) else no swizzle.  `map` points to a CUtensorMap (128 bytes,
+// 64-byte aligned).  cuTensorMapEncodeTiled is resolved through the runtime, so the library has no link-time dependency
+// on libcuda.so (it must load on boxes without a driver: tests/test_cabi.py).
+int make_tensor_map_2d(void* map, const float* base, int64_t outer, int64_t inner, int box_outer, int box_inner,
+                       bool swizzle128, const char* who);
+
 // tile-staged aggregation kernel (spmm_tile.cu)
 bool spmm_tile_supported(int64_t n, int C);
-int spmm_tile_set(int on);
+int spmm_tile_set(int setting);   // mode | flags << 4, see spmm_tile.cu
+int spmm_flags();
 int spmm_bn_bwd_tile_rows(int C);
 int spmm_bn_bwd_tile_launch(const int* rowptr, const int* col, const float* w, const float* gX, const float* Y,
                             const float* mean, const float* rstd, const float* scale, const float* shift,

@@ -18,6 +18,7 @@ int tc_gemm_xw(const float*, const int32_t*, const float*, const float*, float, 
                int64_t, int32_t, int32_t, const float*, int64_t, cudaStream_t);
 int tc_gemm_dx(const float*, const float*, float*, void*, int64_t, int64_t, int32_t, int32_t, const float*, int64_t,
                cudaStream_t);
+namespace tc { int f16_flags(int set); }
 int64_t tc_gemm_dw_workspace_bytes(int64_t, int32_t, int32_t);
 int tc_gemm_dw(const float*, const float*, const int32_t*, const float*, const float*, float, float*, void*,
                int64_t, int64_t, int32_t, int32_t, const float*, int64_t, const float*, int64_t, cudaStream_t);
@@ -43,6 +44,15 @@ static int tc_gemm_dw(const float*, const float*, const int32_t*, const float*, 
 }  // namespace ddmp
 
 extern "C" {
+
+int ddmp_gemm_tc_flags(int flags) {
+#ifdef DDMP_WITH_TC
+    return ddmp::tc::f16_flags(flags);
+#else
+    (void)flags;
+    return 0;
+#endif
+}
 
 int64_t ddmp_gemm_workspace_bytes(int64_t n, int32_t Cin, int32_t Cout) {
     using namespace ddmp;

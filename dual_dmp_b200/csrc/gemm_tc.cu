@@ -14,9 +14,11 @@
 // One elected thread issues the MMAs; `full`/`empty` mbarriers per smem stage; tcgen05.commit releases a stage /
 // publishes the accumulator; dedicated warps drain the double-buffered TMEM accumulator.  CTA pairs (cta_group::2)
 // where the shapes allow.  Kernel inventory and measured behaviour: DESIGN.md §4.2, profiles/README.md.
+#include <cuda.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
+#include <atomic>
 #include <type_traits>
 
 #include "common.cuh"
@@ -1304,6 +1306,69 @@ __device__ __forceinline__ void epilogue_tile(const Args& g, uint32_t taddr, flo
     }
 }
 
+// ---- epilogue through TMA tensor stores (default) -------------------------------------------------------------------
+// The staged epilogue above spends 70 % of its 11-13 k cycles per 128 x 256 tile moving the staging tile to global memory
+// with ld.shared + st.global from 4 warps that share the LSU with the 8 producer warps -- which is what bounds every
+// K <= 256 shape (4 k-blocks of ~1.5 k cycles per tile).  Here a warp writes its 32 x 32 block (already unscaled) into a
+// 128-byte-swizzled 4 KB staging buffer and ONE lane hands it to the TMA unit (cp.async.bulk.tensor.2d.global.shared::cta,
+// SASS UTMASTG; tensor map of C with box 32 x 32 fp32, SWIZZLE_128B; rows past M are clipped by the unit).  Two staging
+// buffers per warp: the next block is written while the previous one is being read out.  A lane owns a ROW here, so it
+// needs the unscale factors of all 32 columns of the block: eight warp-uniform 16-byte loads of inv_sw (one transaction
+// each, L1-resident) issued before the TMEM load is awaited; powers of two, so the products equal the staged path's.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src_smem, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(c0),
+                 "r"(c1), "r"(src_smem)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+constexpr uint32_t kStageWarpBytes = 2u * 32u * 128u;          // two 32 x 128 B staging buffers per epilogue warp
+constexpr uint32_t kStagingBytes = 4u * kStageWarpBytes;       // 32 KB
+
+__device__ __forceinline__ void store_block32_tma(const CUtensorMap* cmap, const uint32_t (&v)[32],
+                                                  const float4 (&cs)[8], float inv_sa, uint32_t stg, int lane, int mrow0,
+                                                  int ncol0) {
+    if (lane == 0) bulk_wait_read1();                // the store that read this buffer two blocks ago has drained it
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i)                      // row = lane, 16-byte chunk i -> swizzled chunk i ^ (lane & 7)
+        sts128(stg + (uint32_t)lane * 128u + (uint32_t)((i ^ (lane & 7)) << 4),
+               make_uint4(__float_as_uint(__uint_as_float(v[4 * i]) * (cs[i].x * inv_sa)),
+                          __float_as_uint(__uint_as_float(v[4 * i + 1]) * (cs[i].y * inv_sa)),
+                          __float_as_uint(__uint_as_float(v[4 * i + 2]) * (cs[i].z * inv_sa)),
+                          __float_as_uint(__uint_as_float(v[4 * i + 3]) * (cs[i].w * inv_sa))));
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+        tma_store_2d(cmap, stg, ncol0, mrow0);
+        bulk_commit();
+    }
+}
+// stg: this warp's two staging buffers (1024-byte aligned); inv_sw: 1 / (scale of weight row n), 16-byte aligned
+template <int BN>
+__device__ __forceinline__ void epilogue_tile_tma(const CUtensorMap* cmap, const float* __restrict__ inv_sw, uint32_t taddr,
+                                                  float inv_sa, uint32_t stg, int lane, int64_t mrow0, int n0) {
+    static_assert(BN % 64 == 0, "two 32-column blocks per iteration");
+    uint32_t va[32], vb[32];
+    float4 cs[8];
+    tmem_ld32_async(taddr, va);
+#pragma unroll 1
+    for (int cb = 0; cb < BN; cb += 64) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cs[i] = ldg4(inv_sw + n0 + cb + 4 * i);
+        tmem_wait_ld();                                  // va has landed
+        tmem_ld32_async(taddr + (uint32_t)cb + 32u, vb);
+        store_block32_tma(cmap, va, cs, inv_sa, stg, lane, (int)mrow0, n0 + cb);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cs[i] = ldg4(inv_sw + n0 + cb + 32 + 4 * i);
+        tmem_wait_ld();                                  // vb has landed
+        if (cb + 64 < BN) tmem_ld32_async(taddr + (uint32_t)cb + 64u, va);
+        store_block32_tma(cmap, vb, cs, inv_sa, stg + 32u * 128u, lane, (int)mrow0, n0 + cb + 32);
+    }
+}
+
 // W [N,K] (or, transposed, W^T given as [K,N]) -> per-row scaled fp16 hi/lo image; one warp per weight row n
 __global__ void tc_prep_b16_kernel(const float* __restrict__ W, int transposed, uint8_t* __restrict__ img,
                                    float* __restrict__ inv_sw, int N, int K, int BN) {
@@ -1353,20 +1418,21 @@ __global__ void tc_prep_b16_kernel(const float* __restrict__ W, int transposed, 
 }
 
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(kV2Threads, 1) tc_gemm_nt16_kernel(const Nt16Args g) {
+__global__ void __launch_bounds__(kV2Threads, 1) tc_gemm_nt16_kernel(const __grid_constant__ CUtensorMap cmap,
+                                                                     const Nt16Args g) {
     constexpr uint32_t A_BYTES = BM * 128;           // 128 rows x 64 fp16, one of hi / lo
     constexpr uint32_t B_BYTES = BN * 128;
     constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
     constexpr uint32_t TMEM_COLS = 2 * BN;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint8_t* staging = smem + STAGES * STAGE_BYTES;          // 4 epilogue warps x 2 buffers x 32 rows x 128 B (1 KB aligned)
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + kStagingBytes);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* acc_full = empty_bar + STAGES;     // [2]
     uint64_t* acc_empty = acc_full + 2;          // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
     uint32_t* amax_slot = tmem_slot + 1;
-    uint8_t* staging = smem + STAGES * STAGE_BYTES + 256;   // 4 epilogue warps x 32 rows x 128 B
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_kb = g.K / BK16;
@@ -1452,7 +1518,8 @@ __global__ void __launch_bounds__(kV2Threads, 1) tc_gemm_nt16_kernel(const Nt16A
     } else if (warp >= 12) {
         // ===== epilogue: TMEM -> registers (unscale) -> swizzled staging tile -> global =====
         const int q = warp & 3;
-        const uint32_t stg = smem_u32(staging) + (uint32_t)q * (32u * 128u);
+        const uint32_t stg = smem_u32(staging) + (uint32_t)q * kStageWarpBytes;
+        const bool staged = (g.flags & 16) != 0;         // A/B switch: the ld.shared + st.global epilogue
         uint32_t tile_no = 0;
         for (int64_t tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++tile_no) {
             const uint32_t buf = tile_no & 1u;
@@ -1460,11 +1527,14 @@ __global__ void __launch_bounds__(kV2Threads, 1) tc_gemm_nt16_kernel(const Nt16A
             const int n0 = (int)(tile % g.tiles_n) * BN;
             mbar_wait(acc_full + buf, (tile_no >> 1) & 1u);
             tc_fence_after();
-            epilogue_tile<BN>(g, tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN, inv_sa, stg, lane, mrow0, n0);
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
+            if (staged) epilogue_tile<BN>(g, taddr, inv_sa, stg, lane, mrow0, n0);
+            else epilogue_tile_tma<BN>(&cmap, g.inv_sw, taddr, inv_sa, stg, lane, mrow0, n0);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty + buf);
         }
+        if (lane == 0) bulk_wait_all();                  // the staging buffers must outlive the last tensor stores
     }
     __syncthreads();
     if (warp == 8) {
@@ -1475,15 +1545,19 @@ __global__ void __launch_bounds__(kV2Threads, 1) tc_gemm_nt16_kernel(const Nt16A
 
 template <int BN, int STAGES>
 static int launch_nt16(const Nt16Args& g, cudaStream_t st) {
-    constexpr size_t smem = (size_t)STAGES * (2 * BM * 128 + 2 * BN * 128) + 1024 + 256 + 4 * 32 * 128;
+    constexpr size_t smem = (size_t)STAGES * (2 * BM * 128 + 2 * BN * 128) + 1024 + 256 + kStagingBytes;
+    static_assert(smem <= 232448, "shared memory of the fp16-split NT kernel");
     static PerDeviceOnce configured;
     if (configured.need()) {
         DDMP_CUDA(cudaFuncSetAttribute(tc_gemm_nt16_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
         configured.mark();
     }
+    CUtensorMap cmap;                                    // result tensor [M, N], 32 x 32 boxes, 128-byte swizzle
+    int rc = make_tensor_map_2d(&cmap, g.C, g.M, g.N, 32, 32, true, "tc_gemm_nt16");
+    if (rc != DDMP_OK) return rc;
     const int64_t grid = g.num_tiles < kNumSMs ? g.num_tiles : kNumSMs;
-    tc_gemm_nt16_kernel<BN, STAGES><<<(unsigned)grid, kV2Threads, smem, st>>>(g);
+    tc_gemm_nt16_kernel<BN, STAGES><<<(unsigned)grid, kV2Threads, smem, st>>>(cmap, g);
     return check_launch("tc_gemm_nt16");
 }
 
@@ -1505,7 +1579,8 @@ __device__ __forceinline__ void umma_f16_2cta(uint32_t tmem_d, uint64_t adesc, u
 
 constexpr int kNt16x2Stages = 3;
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kV2Threads, 1) tc_gemm_nt16x2_kernel(const Nt16Args g) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kV2Threads, 1)
+tc_gemm_nt16x2_kernel(const __grid_constant__ CUtensorMap cmap, const Nt16Args g) {
     constexpr int STAGES = kNt16x2Stages;
     constexpr int BN = 256;
     constexpr uint32_t A_BYTES = BM * 128;
@@ -1515,14 +1590,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kV2Threads, 1) tc_ge
     constexpr uint32_t TMEM_COLS = 2 * BN;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint8_t* staging = smem + STAGES * STAGE_BYTES;          // 1 KB aligned (128-byte swizzle of the tensor stores)
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + kStagingBytes);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* peer_ready = empty_bar + STAGES;
     uint64_t* acc_full = peer_ready + STAGES;
     uint64_t* acc_empty = acc_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
     uint32_t* amax_slot = tmem_slot + 1;
-    uint8_t* staging = smem + STAGES * STAGE_BYTES + 256;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -1635,7 +1710,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kV2Threads, 1) tc_ge
         __syncwarp();
     } else if (warp >= 12) {
         const int q = warp & 3;
-        const uint32_t stg = smem_u32(staging) + (uint32_t)q * (32u * 128u);
+        const uint32_t stg = smem_u32(staging) + (uint32_t)q * kStageWarpBytes;
+        const bool staged = (g.flags & 16) != 0;         // A/B switch: the ld.shared + st.global epilogue
         uint32_t tile_no = 0;
         for (int64_t tile = pair; tile < g.num_tiles; tile += num_pairs, ++tile_no) {
             const uint32_t buf = tile_no & 1u;
@@ -1647,7 +1723,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kV2Threads, 1) tc_ge
             mbar_wait_cluster(acc_full + buf, (tile_no >> 1) & 1u);
             if (tr) e1 = clock64();
             tc_fence_after();
-            epilogue_tile<BN>(g, tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN, inv_sa, stg, lane, mrow0, n0);
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
+            if (staged) epilogue_tile<BN>(g, taddr, inv_sa, stg, lane, mrow0, n0);
+            else epilogue_tile_tma<BN>(&cmap, g.inv_sw, taddr, inv_sa, stg, lane, mrow0, n0);
             tc_fence_before();
             __syncwarp();
             if (tr) {
@@ -1660,6 +1738,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kV2Threads, 1) tc_ge
                 else mbar_arrive_remote(acc_empty + buf, 0);
             }
         }
+        if (lane == 0) bulk_wait_all();                  // the staging buffers must outlive the last tensor stores
     }
     tc_fence_before();
     cluster_sync_all();
@@ -1670,7 +1749,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kV2Threads, 1) tc_ge
 }
 
 static int launch_nt16x2(const Nt16Args& g0, cudaStream_t st) {
-    constexpr size_t smem = (size_t)kNt16x2Stages * (2 * BM * 128 + 2 * 128 * 128) + 1024 + 256 + 4 * 32 * 128;
+    constexpr size_t smem = (size_t)kNt16x2Stages * (2 * BM * 128 + 2 * 128 * 128) + 1024 + 256 + kStagingBytes;
+    static_assert(smem <= 232448, "shared memory of the CTA-pair fp16-split NT kernel");
     static PerDeviceOnce configured;
     if (configured.need()) {
         DDMP_CUDA(cudaFuncSetAttribute(tc_gemm_nt16x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1678,9 +1758,26 @@ static int launch_nt16x2(const Nt16Args& g0, cudaStream_t st) {
     }
     Nt16Args g = g0;
     g.num_tiles = ceil_div(g.M, 2 * BM) * g.tiles_n;
+    CUtensorMap cmap;                                    // result tensor [M, N], 32 x 32 boxes, 128-byte swizzle
+    int rc = make_tensor_map_2d(&cmap, g.C, g.M, g.N, 32, 32, true, "tc_gemm_nt16x2");
+    if (rc != DDMP_OK) return rc;
     const int64_t pairs = g.num_tiles < kNumSMs / 2 ? g.num_tiles : kNumSMs / 2;
-    tc_gemm_nt16x2_kernel<<<(unsigned)(2 * pairs), kV2Threads, smem, st>>>(g);
+    tc_gemm_nt16x2_kernel<<<(unsigned)(2 * pairs), kV2Threads, smem, st>>>(cmap, g);
     return check_launch("tc_gemm_nt16x2");
+}
+
+// switches of the fp16-split NT kernels (environment DDMP_TC_F16_FLAGS, ddmp_gemm_tc_flags): bit 0 = prefetch the next
+// tile's A rows into L2, bit 3 = unstaged epilogue, bit 4 = staged ld.shared + st.global epilogue instead of TMA stores
+int f16_flags(int set) {
+    static std::atomic<int> v{-1};
+    int cur = v.load(std::memory_order_relaxed);
+    if (cur < 0) {
+        const char* e = getenv("DDMP_TC_F16_FLAGS");
+        cur = e ? (atoi(e) & 0xffff) : 0;
+        v.store(cur, std::memory_order_relaxed);
+    }
+    if (set >= 0) v.store(set & 0xffff, std::memory_order_relaxed);
+    return cur;
 }
 
 static bool f16_split_enabled() {
@@ -1700,8 +1797,7 @@ static int run_nt16(const float* A, const int* a_map, const float* scale, const 
     Nt16Args g{};
     g.A = A; g.Bimg = img; g.inv_sw = inv_sw; g.C = C; g.a_map = a_map; g.scale = scale; g.shift = shift;
     g.slope = slope; g.amax = amax; g.amax_len = amax_len;
-    static const int flags = [] { const char* e = getenv("DDMP_TC_F16_FLAGS"); return e ? atoi(e) : 0; }();
-    g.flags = flags;
+    g.flags = f16_flags(-1);
     static const bool trace = [] { const char* e = getenv("DDMP_TC_TRACE"); return e && e[0] == '1'; }();
     static unsigned long long* trace_buf = nullptr;
     if (trace) {

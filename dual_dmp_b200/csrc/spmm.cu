@@ -19,7 +19,7 @@ __global__ void __launch_bounds__(256, (STATS || C >= 512) ? 3 : 4)
 spmm_gcn_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const float* __restrict__ w,
                 const float* __restrict__ H, const float* __restrict__ bias, float* __restrict__ Y,
                 float* __restrict__ partials, float* __restrict__ amax_blocks, int64_t n, int rows_per_block,
-                int blocks_per_cta) {
+                int blocks_per_cta, int flags) {
     constexpr int G = (C / 4 < 32) ? (C / 4) : 32;
     constexpr int NV = C / (4 * G);
     constexpr int GROUPS = 256 / G;
@@ -146,7 +146,8 @@ spmm_gcn_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, con
             if (BIAS) {
                 o.x += bsum[v].x; o.y += bsum[v].y; o.z += bsum[v].z; o.w += bsum[v].w;
             }
-            st4(yp + (v * G + lg) * 4, o);
+            if (flags & 2) __stcs(reinterpret_cast<float4*>(yp + (v * G + lg) * 4), o);   // streaming: Y is not re-read from L2
+            else st4(yp + (v * G + lg) * 4, o);
             amx = fmaxf(fmaxf(amx, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
             if (STATS) {                            // Welford: running mean and M2 of this group's rows (see bn.cu)
                 float4 s = *reinterpret_cast<float4*>(myred + (v * G + lg) * 4);
@@ -381,12 +382,13 @@ static int launch_spmm(const int* rowptr, const int* col, const float* w, const 
     int bpc = chunk_env < 1 ? 1 : chunk_env;
     while (bpc > 1 && ceil_div(nblk, bpc) < 8 * kNumSMs) --bpc;
     const unsigned grid = (unsigned)ceil_div(nblk, bpc);
+    const int fl = spmm_flags();
     if (partials) {
-        if (bias) spmm_gcn_kernel<C, true, true><<<grid, 256, 0, st>>>(rowptr, col, w, H, bias, Y, partials, amax_blocks, n, rpb, bpc);
-        else spmm_gcn_kernel<C, true, false><<<grid, 256, 0, st>>>(rowptr, col, w, H, bias, Y, partials, amax_blocks, n, rpb, bpc);
+        if (bias) spmm_gcn_kernel<C, true, true><<<grid, 256, 0, st>>>(rowptr, col, w, H, bias, Y, partials, amax_blocks, n, rpb, bpc, fl);
+        else spmm_gcn_kernel<C, true, false><<<grid, 256, 0, st>>>(rowptr, col, w, H, bias, Y, partials, amax_blocks, n, rpb, bpc, fl);
     } else {
-        if (bias) spmm_gcn_kernel<C, false, true><<<grid, 256, 0, st>>>(rowptr, col, w, H, bias, Y, partials, amax_blocks, n, rpb, bpc);
-        else spmm_gcn_kernel<C, false, false><<<grid, 256, 0, st>>>(rowptr, col, w, H, bias, Y, partials, amax_blocks, n, rpb, bpc);
+        if (bias) spmm_gcn_kernel<C, false, true><<<grid, 256, 0, st>>>(rowptr, col, w, H, bias, Y, partials, amax_blocks, n, rpb, bpc, fl);
+        else spmm_gcn_kernel<C, false, false><<<grid, 256, 0, st>>>(rowptr, col, w, H, bias, Y, partials, amax_blocks, n, rpb, bpc, fl);
     }
     return check_launch("spmm_gcn");
 }

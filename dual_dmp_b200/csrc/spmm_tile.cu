@@ -385,47 +385,8 @@ constexpr size_t smem_bytes() {
     return 128 + (size_t)R * CS * 4 + (size_t)R * kMetaPerRow * 8 + (size_t)(R + 4) * 4 + 8 + (kThreads / 32) * 4 + 16;
 }
 
-typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-// cuTensorMapEncodeTiled is resolved through the runtime (cudaGetDriverEntryPoint), so the library has no link-time
-// dependency on libcuda.so (it must load on boxes without a driver: tests/test_cabi.py).
-static EncodeFn encode_fn() {
-    static EncodeFn fn = [] {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
-            q != cudaDriverEntryPointSuccess)
-            p = nullptr;
-        return reinterpret_cast<EncodeFn>(p);
-    }();
-    return fn;
-}
-
 static int make_map(CUtensorMap* map, const float* H, int64_t n, int C, int CS, int R) {
-    // the driver call needs a current context on THIS thread: the autograd engine's thread may reach the first
-    // aggregation of a backward pass before any runtime call has bound the primary context to it
-    static thread_local const bool bound = (cudaFree(nullptr), true);
-    (void)bound;
-    EncodeFn enc = encode_fn();
-    if (!enc) {
-        set_error("spmm_tile: cuTensorMapEncodeTiled is not available from this driver");
-        return DDMP_ERR_CUDA;
-    }
-    const cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)n};
-    const cuuint64_t strides[1] = {(cuuint64_t)C * 4};
-    const cuuint32_t box[2] = {(cuuint32_t)CS, (cuuint32_t)R};
-    const cuuint32_t estr[2] = {1, 1};
-    CUresult rc = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(H), dims, strides, box, estr,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (rc != CUDA_SUCCESS) {
-        set_error("spmm_tile: cuTensorMapEncodeTiled failed (CUresult %d) for H=%p n=%lld C=%d box=%dx%d", (int)rc,
-                  (const void*)H, (long long)n, C, R, CS);
-        return DDMP_ERR_CUDA;
-    }
-    return DDMP_OK;
+    return make_tensor_map_2d(map, H, n, C, R, CS, false, "spmm_tile");
 }
 
 template <int CS, int R>
@@ -495,25 +456,33 @@ int spmm_bn_bwd_tile_launch(const int* rowptr, const int* col, const float* w, c
     return tile::launch_bwd<128, 64>(a, st);
 }
 
-// 0 = gather kernel for every width, 1 = tile-staged kernel where it measures faster (C <= 128: B200, 1M-face graphs,
-// profiles/spmm_tile_ab_r2.txt), 2 = tile-staged kernel for every supported width.  -1: not decided yet (environment
-// DDMP_SPMM_TILE, default 1).
+// Kernel choice (ddmp_spmm_use_tile_kernel(v) / environment DDMP_SPMM_TILE; v = mode | flags << 4):
+//   mode 0 = gather kernel for every width
+//        1 = tile-staged kernel for C <= 128, gather kernel above (default: measured fastest on B200, 1M-face graphs,
+//            profiles/spmm_tile_ab_r2.txt, profiles/spmm_pipe_ab_r2.txt)
+//        2 = tile-staged kernel for every supported width
+//   flags bit 1 = streaming (evict-first) stores of Y in the gather kernel (default on: Y is never re-read from L2 by this
+//   kernel, and keeping it out leaves the cache to the gathered rows: +1 % on the wide layers).  -1: not decided yet.
 static std::atomic<int> g_tile_mode{-1};
+constexpr int kDefaultSetting = 1 | (2 << 4);
 
-static int tile_mode() {
+static int tile_setting() {
     int v = g_tile_mode.load(std::memory_order_relaxed);
     if (v < 0) {
         const char* e = getenv("DDMP_SPMM_TILE");
-        v = e ? atoi(e) : 1;
-        if (v < 0 || v > 2) v = 1;
+        v = e ? atoi(e) : kDefaultSetting;
+        if (v < 0 || (v & 15) > 2) v = kDefaultSetting;
         g_tile_mode.store(v, std::memory_order_relaxed);
     }
     return v;
 }
+static int tile_mode() { return tile_setting() & 15; }
+int spmm_flags() { return tile_setting() >> 4; }
 
-int spmm_tile_set(int mode) {
-    const int prev = tile_mode();
-    g_tile_mode.store(mode < 0 ? 0 : (mode > 2 ? 2 : mode), std::memory_order_relaxed);
+int spmm_tile_set(int v) {
+    const int prev = tile_setting();
+    if (v < 0 || (v & 15) > 2) v = kDefaultSetting;
+    g_tile_mode.store(v, std::memory_order_relaxed);
     return prev;
 }
 

@@ -74,9 +74,10 @@ int ddmp_spmm_gcn(const int32_t* rowptr, const int32_t* col, const float* w, con
                   float* Y, float* stats_partials, float* amax_blocks, int64_t n, int32_t C, void* stream);
 /* number of floats ddmp_spmm_gcn writes to amax_blocks for this shape */
 int64_t ddmp_spmm_amax_len(int64_t n, int32_t C);
-/* Kernel choice of ddmp_spmm_gcn (environment DDMP_SPMM_TILE, default 1): 0 = gather-only kernel for every width,
- * 1 = tile-staged kernel for C <= 128 (where it measures faster on B200), 2 = tile-staged kernel for every mesh width
- * (A/B measurements, bit-exactness test between the two kernels).  Returns the previous setting. */
+/* Kernel choice of ddmp_spmm_gcn (environment DDMP_SPMM_TILE, default 33).  setting = mode | flags << 4.
+ * mode: 0 = gather-only kernel for every width, 1 = tile-staged kernel for C <= 128 (where it measures faster on B200),
+ * 2 = tile-staged kernel for every mesh width (A/B measurements, bit-exactness test between the two kernels).
+ * flags: bit 1 = streaming stores of Y in the gather kernel.  Returns the previous setting. */
 int ddmp_spmm_use_tile_kernel(int mode);
 
 /* Backward aggregation fused with ddmp_bn_bwd_apply:  dH = A_hat * dY  with dY recomputed on the fly from the gathered
@@ -158,6 +159,10 @@ int ddmp_gemm_xw(const float* X, const int32_t* row_map, const float* scale, con
 /* scratch the tensor-core path of gemm_xw / gemm_dx needs for the pre-split, pre-swizzled weight image (0 when the
  * shape runs on the FFMA kernel; with workspace == NULL the FFMA kernel is used). */
 int64_t ddmp_gemm_workspace_bytes(int64_t n, int32_t Cin, int32_t Cout);
+/* A/B switches of the fp16-split tcgen05 kernels behind ddmp_gemm_xw / ddmp_gemm_dx (environment DDMP_TC_F16_FLAGS,
+ * default 0): bit 0 = prefetch the next tile's rows into L2, bit 3 = unstaged epilogue, bit 4 = staged ld.shared +
+ * st.global epilogue instead of TMA tensor stores.  flags < 0 only queries.  Returns the previous value. */
+int ddmp_gemm_tc_flags(int flags);
 /* gX[n,Cin] = dH[n,Cout] * W[Cout,Cin]. */
 int ddmp_gemm_dx(const float* dH, const float* W, float* gX, void* workspace, int64_t workspace_bytes, int64_t n,
                  int32_t Cin, int32_t Cout, const float* amax, int64_t amax_len, int backend, void* stream);

@@ -199,19 +199,59 @@ def test_batchnorm_statistics_with_large_mean_over_sigma(C, n, ratio):
     ref_var = Yd.double().var(0, unbiased=False)
     gamma, beta = torch.ones(C, device=DEV), torch.zeros(C, device=DEV)
     tol = 2e-6 + 4e-7 * ratio
+    prev = lib.query("ddmp_spmm_use_tile_kernel", 0)
     try:
-        for mode in (2, 0):
+        for mode in (2, 0, 2 | (2 << 4), 2 << 4):    # tile-staged / gather kernel, without and with streaming stores
             lib.query("ddmp_spmm_use_tile_kernel", mode)
             _, partials = F_.spmm_gcn(graph, Yd, stats=True)
             st = F_.bn_stats_finalize(partials, n, gamma, beta)
             e_mean = float((st[0].double() - ref_mean).abs().max() / ref_mean.abs().max().clamp_min(1.0))
             e_rstd = rel_err(st[1], torch.rsqrt(ref_var + 1e-5))
             st2 = F_.bn_stats_finalize_sums(F_.bn_rank_sums(partials, n), n, gamma, beta)
-            report(f"bn stats |mean|/sigma={ratio:g} C={C} n={n} kernel mode {mode}", (e_mean, e_rstd))
+            report(f"bn stats |mean|/sigma={ratio:g} C={C} n={n} kernel setting {mode}", (e_mean, e_rstd))
             assert e_mean < 2e-7 and e_rstd < tol, (mode, e_mean, e_rstd, tol)
             assert torch.equal(st, st2)
     finally:
-        lib.query("ddmp_spmm_use_tile_kernel", 1)
+        lib.query("ddmp_spmm_use_tile_kernel", prev)
+
+
+@pytest.mark.parametrize("cin,cout", [(64, 128), (128, 256), (256, 256), (512, 512), (512, 256), (256, 64), (128, 64)])
+@pytest.mark.parametrize("n", [37, 640, 4099, 77777])
+def test_gemm_f16_split_tma_epilogue_equals_staged_epilogue(cin, cout, n):
+    """The fp16-split NT kernels write their result with TMA tensor stores (32 x 32 boxes out of a 128-byte-swizzled
+    staging buffer, rows past n clipped by the unit); the staged ld.shared + st.global epilogue stays behind
+    ddmp_gemm_tc_flags(16).  Same accumulators, same power-of-two unscale: the two must be IDENTICAL -- row counts below
+    one box, not a multiple of 32, and many tiles per CTA; no write may land past row n."""
+    from dual_dmp_b200 import functional as F_
+    from dual_dmp_b200._lib import lib
+    torch.manual_seed(cin + cout + n)
+    X = (torch.randn(n, cin) * (torch.rand(1, cin) * 3 + 0.1)).to(DEV)
+    W = (torch.randn(cout, cin) / cin ** 0.5).to(DEV)
+    W[1] *= 1e-5
+    sc, sh = (torch.rand(cin) + 0.5).to(DEV), torch.randn(cin).to(DEV)
+    dH = (torch.randn(n, cout) * 1e-3).to(DEV)
+    b_act = (torch.nn.functional.leaky_relu(X * sc + sh, 0.01).abs().amax(0) * 1.5).contiguous()
+    b_dh = dH.abs().amax(0).contiguous()
+    prev = lib.query("ddmp_gemm_tc_flags", -1)
+    try:
+        res = {}
+        for fl in (16, 0):
+            lib.query("ddmp_gemm_tc_flags", fl)
+            # outputs are views of larger poisoned buffers: a store past row n would be seen
+            Hbuf = torch.full((n + 64, cout), 7.0, device=DEV)
+            Gbuf = torch.full((n + 64, cin), 7.0, device=DEV)
+            F_.gemm_xw(X, W, scale=sc, shift=sh, backend=2, amax=b_act, out=Hbuf[:n])
+            F_.gemm_dx(dH, W, backend=2, amax=b_dh, out=Gbuf[:n])
+            assert (Hbuf[n:] == 7.0).all() and (Gbuf[n:] == 7.0).all()
+            res[fl] = (Hbuf[:n].clone(), Gbuf[:n].clone())
+        assert torch.equal(res[0][0], res[16][0])
+        assert torch.equal(res[0][1], res[16][1])
+        act = torch.nn.functional.leaky_relu(X.double() * sc.double() + sh.double(), 0.01)
+        assert rel_err(res[0][0], act @ W.double().t()) < 5e-6
+        assert rel_err(res[0][1], dH.double() @ W.double()) < 5e-6
+        assert rel_err(res[0][0][:, 1], act @ W[1].double()) < 5e-6       # a weight row 1e-5 of its tile's maximum
+    finally:
+        lib.query("ddmp_gemm_tc_flags", prev)
 
 
 @pytest.mark.parametrize("kind", [0, 1])
@@ -461,18 +501,20 @@ def test_spmm_tile_kernel_equals_gather_kernel_bitwise(kind, n, C):
                GcnGraph(ds.face_index, F, DEV, coords=ds.z2.detach()[:, :3], reorder=True),
                GcnGraph(ds.face_index, F, DEV, reorder=False)]
     torch.manual_seed(C + n)
+    prev = lib.query("ddmp_spmm_use_tile_kernel", 0)
     try:
         for graph in graphs_:
             H = torch.randn(graph.n, C, device=DEV)
             b = torch.randn(C, device=DEV)
             res = {}
-            for on in (2, 0):
+            for on in (2, 0, 2 << 4):                # tile-staged, gather, gather with streaming stores
                 lib.query("ddmp_spmm_use_tile_kernel", on)
                 Y, partials, ab = F_.spmm_gcn(graph, H, bias=b, stats=True, amax=True)
                 Yp = F_.spmm_gcn(graph, H)
                 res[on] = (Y, partials, ab.max(), Yp)
             assert torch.equal(res[2][0], res[0][0]) and torch.equal(res[2][3], res[0][3])
             assert torch.equal(res[2][1], res[0][1])
+            assert torch.equal(res[32][0], res[0][0]) and torch.equal(res[32][3], res[0][3]) and torch.equal(res[32][1], res[0][1])
             assert float(res[2][2]) == float(res[0][2]) == float(res[0][0].abs().max())
             # partitioned layout: the last rows of H are "halo" rows that are only read
             n_own = graph.n - max(1, graph.n // 7)
@@ -485,7 +527,7 @@ def test_spmm_tile_kernel_equals_gather_kernel_bitwise(kind, n, C):
             assert outs[0].shape == (n_own, C) and torch.equal(outs[0], outs[1])
             assert torch.equal(outs[0], res[0][0][:n_own])
     finally:
-        lib.query("ddmp_spmm_use_tile_kernel", 1)
+        lib.query("ddmp_spmm_use_tile_kernel", prev)
 
 
 @pytest.mark.parametrize("C", [32, 64, 128, 256, 512])
