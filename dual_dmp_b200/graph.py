@@ -39,6 +39,45 @@ def morton_order(coords: np.ndarray) -> np.ndarray:
     return np.argsort(code, kind="stable").astype(np.int64)
 
 
+def hilbert_order(coords: np.ndarray, bits: int = 20) -> np.ndarray:
+    """Permutation (new -> old) that sorts points along a 3-D Hilbert curve (``bits`` bits per axis, Skilling's
+    axes-to-transpose construction, vectorised); ties broken by original id.  Consecutive cells of a Hilbert curve are
+    always face-adjacent, so a run of consecutive rows is one connected patch -- a Morton run falls apart into distant
+    pieces wherever it crosses a high-order cell boundary, and the rows gathered across such a break miss L2."""
+    c = np.asarray(coords, dtype=np.float64)
+    lo, hi = c.min(axis=0), c.max(axis=0)
+    span = np.where(hi > lo, hi - lo, 1.0)
+    q = np.floor((c - lo) / span * float((1 << bits) - 1)).astype(np.uint64)
+    X = [q[:, 0].copy(), q[:, 1].copy(), q[:, 2].copy()]
+    one = np.uint64(1)
+    Q = one << np.uint64(bits - 1)
+    while Q > one:                                   # inverse undo
+        P = Q - one
+        for i in range(3):
+            hit = (X[i] & Q) != 0
+            t = np.where(hit, np.uint64(0), (X[0] ^ X[i]) & P)
+            X[0] = np.where(hit, X[0] ^ P, X[0] ^ t)
+            X[i] = X[i] ^ t
+        Q >>= one
+    X[1] ^= X[0]                                     # Gray encode
+    X[2] ^= X[1]
+    t = np.zeros_like(X[0])
+    Q = one << np.uint64(bits - 1)
+    while Q > one:
+        t = np.where((X[2] & Q) != 0, t ^ (Q - one), t)
+        Q >>= one
+    code = (_part1by2(X[0] ^ t) << np.uint64(2)) | (_part1by2(X[1] ^ t) << np.uint64(1)) | _part1by2(X[2] ^ t)
+    return np.argsort(code, kind="stable").astype(np.int64)
+
+
+def sfc_order(coords: np.ndarray) -> np.ndarray:
+    """Row order of the reordered graphs: Hilbert curve by default, ``DDMP_SFC=morton`` for the Z-order curve."""
+    import os
+    if os.environ.get("DDMP_SFC", "hilbert").lower() == "morton":
+        return morton_order(coords)
+    return hilbert_order(coords)
+
+
 class GcnGraph:
     """Device-resident normalised adjacency of one graph (vertex graph or face-adjacency graph)."""
 
@@ -52,7 +91,7 @@ class GcnGraph:
         self.device = torch.device(device)
         if reorder and coords is not None:
             c = coords.detach().cpu().numpy() if isinstance(coords, torch.Tensor) else np.asarray(coords)
-            perm = morton_order(c[:, :3])
+            perm = sfc_order(c[:, :3])
         else:
             perm = np.arange(n, dtype=np.int64)
         inv = np.empty(n, dtype=np.int64)

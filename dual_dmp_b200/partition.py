@@ -24,7 +24,7 @@ import torch
 import torch.distributed as dist
 
 from ._lib import lib, ptr, set_device, stream_ptr
-from .graph import morton_order
+from .graph import sfc_order
 
 
 def split_bounds(n: int, world: int) -> np.ndarray:
@@ -42,7 +42,7 @@ class PartitionPlan:
         n = int(num_nodes)
         c = coords.detach().cpu().numpy() if isinstance(coords, torch.Tensor) else np.asarray(coords)
         self.n, self.world = n, int(world)
-        self.perm = morton_order(c[:, :3])                  # new -> old
+        self.perm = sfc_order(c[:, :3])                     # new -> old
         inv = np.empty(n, dtype=np.int64)
         inv[self.perm] = np.arange(n, dtype=np.int64)
         self.inv = inv

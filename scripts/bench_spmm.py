@@ -22,7 +22,7 @@ for name, g in (("vertex", vg), ("face", fg)):
     for C in (32, 64, 128, 256, 512):
         H = torch.randn(g.n, C, device=dev); b = torch.randn(C, device=dev)
         byt = 4 * ((g.n + 1) + 2 * g.nnz + 2 * g.n * C)
-        for flav, fn in (("fwd(stats+bias)", lambda: F_.spmm_gcn(g, H, bias=b, stats=True, amax=True)), ("bwd(plain)", lambda: F_.spmm_gcn(g, H, amax=True))):
+        for flav, fn in (("fwd(stats+bias)", lambda: F_.spmm_gcn(g, H, bias=b, stats=True)), ("bwd(plain)", lambda: F_.spmm_gcn(g, H, amax=True))):
             line = f"{name:6s} C={C:3d} {flav:16s}"
             for s in settings:
                 lib.query("ddmp_spmm_use_tile_kernel", s)

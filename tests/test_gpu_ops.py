@@ -530,6 +530,50 @@ def test_spmm_tile_kernel_equals_gather_kernel_bitwise(kind, n, C):
         lib.query("ddmp_spmm_use_tile_kernel", prev)
 
 
+@pytest.mark.parametrize("C", [256, 512])
+@pytest.mark.parametrize("kind,n", [("ico", 3), ("open", 9), ("ico", 40)])
+def test_spmm_channel_sliced_kernel_equals_whole_row_kernel_bitwise(kind, n, C):
+    """spmm_gcn_slice_kernel (wide layers: a CTA owns a 128- or 256-channel slice of its row block, Welford state of the
+    BatchNorm epilogue in registers; flags 4 / 8 / 16 / 32 of ddmp_spmm_use_tile_kernel) walks the rows of a block with
+    the same warp -> row assignment, the same per-element accumulation order and the same Chan merge as
+    spmm_gcn_kernel, so Y, the (sum, M2) block partials and max|Y| must be IDENTICAL -- both flavours, with and without
+    bias, ragged last block, partitioned layout ([owned | halo] rows)."""
+    from dual_dmp_b200 import functional as F_
+    from dual_dmp_b200._lib import lib
+    from dual_dmp_b200.graph import GcnGraph
+    from oracle.step_ref import make_dataset
+    n_mesh, s_mesh, _ = small_case(kind, n)
+    ds = make_dataset(n_mesh, s_mesh)
+    V, F = len(n_mesh.vs), len(n_mesh.faces)
+    graphs_ = [GcnGraph(ds.edge_index, V, DEV, coords=ds.x_pos, reorder=True),
+               GcnGraph(ds.face_index, F, DEV, coords=ds.z2.detach()[:, :3], reorder=True)]
+    torch.manual_seed(C + n)
+    prev = lib.query("ddmp_spmm_use_tile_kernel", 0)
+    try:
+        for graph in graphs_:
+            H = torch.randn(graph.n, C, device=DEV)
+            b = torch.randn(C, device=DEV) * 3
+            n_own = graph.n - max(1, graph.n // 7)
+            rp = graph.rowptr[: n_own + 1].contiguous()
+            sub = type("G", (), dict(rowptr=rp, col=graph.col, w=graph.w, rowptr_t=rp, col_t=graph.col, w_t=graph.w))
+            res = {}
+            for flags in (0, 2, 4, 8, 16, 32, 2 | 4 | 16, 2 | 8 | 32, 4 | 32):
+                lib.query("ddmp_spmm_use_tile_kernel", 1 | (flags << 4))
+                Ya, Pa = F_.spmm_gcn(graph, H, bias=b, stats=True)
+                Yb, Pb = F_.spmm_gcn(graph, H, stats=True)
+                Yc, Pc = F_.spmm_gcn(sub, H, bias=b, stats=True, n_rows=n_own)
+                Yd, ab = F_.spmm_gcn(graph, H, amax=True)
+                Ye, Pe, ab2 = F_.spmm_gcn(graph, H, bias=b, stats=True, amax=True)
+                Yf = F_.spmm_gcn(sub, H, n_rows=n_own)
+                res[flags] = (Ya, Pa, Yb, Pb, Yc, Pc, Yd, ab.max(), Ye, Pe, ab2.max(), Yf)
+            assert float(res[0][7]) == float(res[0][6].abs().max())
+            for flags in list(res)[1:]:
+                for i, (x, x0) in enumerate(zip(res[flags], res[0])):
+                    assert torch.equal(x, x0), (flags, i, graph.n, C)
+    finally:
+        lib.query("ddmp_spmm_use_tile_kernel", prev)
+
+
 @pytest.mark.parametrize("C", [32, 64, 128, 256, 512])
 @pytest.mark.parametrize("kind,n,which", [("open", 9, "vg"), ("open", 9, "fg"), ("ico", 3, "fg"), ("ico", 24, "vg"),
                                           ("ico", 24, "fg_id")])
