@@ -45,13 +45,14 @@ struct Args {
     const int* corner_slot;  // [3F]
     // workspace
     float* d;                // [V,3]
+    float* ds;               // [V,4]  residual / degree (16-byte records)
     float* fc;               // [F,3]
     float* fa;               // [F]
     float* wca;              // [F,3]
     float* normals;          // [loop][F,3]   (iteration outputs 1..loop)
     float* g_last;           // [F,3]
     float* g;                // [F,3]
-    float* face_tmp;         // [F,9]
+    float* face_tmp;         // [F,3,4]  per-corner messages of pos_norm (16-byte records)
     float* msg;              // [2][F,9]
     double* partials;        // [kSlots][kMaxBlocks]
     // outputs
@@ -92,18 +93,32 @@ __device__ __forceinline__ void publish(double local, double* partials, int slot
     __syncthreads();
 }
 
-// sum of all blocks' partials of `slot`, in block order, identical in every thread of every block
+// sum of all blocks' partials of `slot`, identical in every thread of every block: lane l of warp 0 adds the partials
+// l, l+32, l+64, ... in ascending order, the 32 lane sums are folded by a fixed shuffle tree.  (One thread adding the
+// ~600 partials in a dependent chain of L2 loads and DADDs took ~15 us per scalar -- six scalars = 30 % of the kernel.)
 __device__ __forceinline__ double total(const double* partials, int slot, double* sm) {
-    double r = 0.0;
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32) {
         const double* p = partials + slot * kMaxBlocks;
-        for (unsigned i = 0; i < gridDim.x; ++i) r += __ldcg(p + i);
-        sm[0] = r;
+        double r = 0.0;
+        for (unsigned i = threadIdx.x; i < gridDim.x; i += 32) r += __ldcg(p + i);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+        if (threadIdx.x == 0) sm[0] = r;
     }
     __syncthreads();
-    r = sm[0];
+    const double r = sm[0];
     __syncthreads();
     return r;
+}
+
+// Phase trace (ddmp_dual_loss_trace): block 0 / thread 0 stamps %globaltimer at the phase boundaries of the last launch.
+__device__ unsigned long long g_trace[16];
+__device__ __forceinline__ void stamp(int i) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_trace[i] = t;
+    }
 }
 
 constexpr float kTwoSigmaS2 = 0.18f;   // 2 * 0.3^2  (reference util/loss.py:110-112)
@@ -121,6 +136,7 @@ dual_loss_kernel(const Args a) {
     const int loop = a.loop;
 
     // ================= P1 =================================================================================
+    stamp(0);
     {
         double acc_pr = 0.0, acc_lap = 0.0;
         STRIDE_LOOP(i, V) {
@@ -132,15 +148,30 @@ dual_loss_kernel(const Args a) {
                 acc_pr += dd * dd;
             }
             const int s = a.lap_rowptr[i], e = a.lap_rowptr[i + 1];
-            for (int k = s; k < e; ++k) {
-                const int64_t j = a.lap_col[k];
-                sx += __ldg(a.pos + 3 * j); sy += __ldg(a.pos + 3 * j + 1); sz += __ldg(a.pos + 3 * j + 2);
+            for (int k0 = s; k0 < e; k0 += 8) {
+                int jj[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) jj[u] = (k0 + u < e) ? a.lap_col[k0 + u] : -1;
+                float vx[8], vy[8], vz[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int64_t j = jj[u] >= 0 ? jj[u] : i;
+                    vx[u] = __ldg(a.pos + 3 * j); vy[u] = __ldg(a.pos + 3 * j + 1); vz[u] = __ldg(a.pos + 3 * j + 2);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (jj[u] >= 0) { sx += vx[u]; sy += vy[u]; sz += vz[u]; }
             }
             const float deg = (float)(e - s);
             const float dx = p[0] - sx / deg, dy = p[1] - sy / deg, dz = p[2] - sz / deg;
             a.d[3 * i] = dx; a.d[3 * i + 1] = dy; a.d[3 * i + 2] = dz;
+            // residual / degree, 16-byte records: what the NEIGHBOURS gather in the backward (one 128-bit load each
+            // instead of two rowptr lookups + three scalar loads)
+            const float inv = 1.0f / deg;
+            reinterpret_cast<float4*>(a.ds)[i] = make_float4(dx * inv, dy * inv, dz * inv, 0.f);
             acc_lap += (double)(dx * dx + dy * dy + dz * dz);
         }
+        stamp(1);
         double acc_nr = 0.0, acc_pn = 0.0;
         const float kpn = a.k[4] / (float)V;                       // gout / V of pos_norm
         const double knr = (double)a.k[2] / (double)F;             // gout / F of norm_rec
@@ -173,8 +204,7 @@ dual_loss_kernel(const Args a) {
 #pragma unroll
             for (int m = 0; m < 3; ++m) {
                 const float coef = kpn * (sg[m] - S / 3.0f);
-#pragma unroll
-                for (int x = 0; x < 3; ++x) a.face_tmp[9 * f + 3 * m + x] = coef * n[x];
+                reinterpret_cast<float4*>(a.face_tmp)[3 * f + m] = make_float4(coef * n[0], coef * n[1], coef * n[2], 0.f);
             }
             // norm_rec forward + backward
 #pragma unroll
@@ -185,18 +215,21 @@ dual_loss_kernel(const Args a) {
                 a.gnrm[3 * f + x] = g_nr + kpn * gn[x];
             }
         }
+        stamp(2);
         publish(acc_pr, a.partials, 0, sm);
         publish(acc_lap, a.partials, 1, sm);
         publish(acc_nr, a.partials, 2, sm);
         publish(acc_pn, a.partials, 3, sm);
     }
     grid.sync();
+    stamp(3);
     const double l1 = sqrt(total(a.partials, 0, sm) / (double)V + 1.0e-6);
     const float l2 = (float)sqrt(total(a.partials, 1, sm) / (double)V + 1.0e-12);
     const double l3 = total(a.partials, 2, sm) / (double)F;
     const float l5 = (float)(total(a.partials, 3, sm) / (double)V);
 
     // ================= P2 =================================================================================
+    stamp(4);
     {
         const double kpr = (double)a.k[0] / ((double)V * l1);
         const float klap = a.k[1] / ((float)V * l2);
@@ -204,16 +237,34 @@ dual_loss_kernel(const Args a) {
             // Laplacian backward (transpose of the row-normalised adjacency: neighbours' residuals / their degree)
             const int s = a.lap_rowptr[i], e = a.lap_rowptr[i + 1];
             float gx = a.d[3 * i], gy = a.d[3 * i + 1], gz = a.d[3 * i + 2];
-            for (int kk = s; kk < e; ++kk) {
-                const int64_t j = a.lap_col[kk];
-                const float inv = 1.0f / (float)(a.lap_rowptr[j + 1] - a.lap_rowptr[j]);
-                gx -= __ldcg(a.d + 3 * j) * inv; gy -= __ldcg(a.d + 3 * j + 1) * inv; gz -= __ldcg(a.d + 3 * j + 2) * inv;
+            // neighbour lists in batches of 8 (predicated): all index loads of a batch, then all gathers, are in flight
+            // together; the sums keep the CSR order
+            for (int k0 = s; k0 < e; k0 += 8) {
+                int jj[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) jj[u] = (k0 + u < e) ? a.lap_col[k0 + u] : -1;
+                float4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    v[u] = (jj[u] >= 0) ? __ldcg(reinterpret_cast<const float4*>(a.ds) + jj[u]) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (jj[u] >= 0) { gx -= v[u].x; gy -= v[u].y; gz -= v[u].z; }
             }
             // corner gather of the pos_norm messages
             float cx = 0.f, cy = 0.f, cz = 0.f;
-            for (int k = a.corner_ptr[i]; k < a.corner_ptr[i + 1]; ++k) {
-                const int64_t sl = a.corner_slot[k];
-                cx += __ldcg(a.face_tmp + 3 * sl); cy += __ldcg(a.face_tmp + 3 * sl + 1); cz += __ldcg(a.face_tmp + 3 * sl + 2);
+            const int cs = a.corner_ptr[i], ce = a.corner_ptr[i + 1];
+            for (int k0 = cs; k0 < ce; k0 += 8) {
+                int sl[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) sl[u] = (k0 + u < ce) ? a.corner_slot[k0 + u] : -1;
+                float4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    v[u] = (sl[u] >= 0) ? __ldcg(reinterpret_cast<const float4*>(a.face_tmp) + sl[u]) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (sl[u] >= 0) { cx += v[u].x; cy += v[u].y; cz += v[u].z; }
             }
             const float g3[3] = {klap * gx, klap * gy, klap * gz};
             const float c3[3] = {cx, cy, cz};
@@ -223,6 +274,7 @@ dual_loss_kernel(const Args a) {
                 a.gpos[3 * i + c] = (g_pr + g3[c]) + c3[c];
             }
         }
+        stamp(5);
         double acc_sig = 0.0;
         if (loop > 0) {
             STRIDE_LOOP(f, F) {
@@ -239,11 +291,13 @@ dual_loss_kernel(const Args a) {
                 }
             }
         }
+        stamp(6);
         publish(acc_sig, a.partials, 4, sm);
     }
     float l4 = 0.f;
     if (loop > 0) {
         grid.sync();
+        stamp(7);
         const float sg = (float)(total(a.partials, 4, sm) / (double)(3 * F));
         const float den = 2.0f * (sg * sg);
         const float kb = (a.k[3] * a.bnf_scale) / (float)F;        // gout / F of the bnf L1 term
@@ -291,6 +345,7 @@ dual_loss_kernel(const Args a) {
                 }
             }
         }
+        stamp(8);
         publish(acc_bnf, a.partials, 5, sm);
 
         // ================= P4: backward of the iterations ===================================================
@@ -335,7 +390,9 @@ dual_loss_kernel(const Args a) {
 #pragma unroll
                 for (int x = 0; x < 3; ++x) a.g[3 * f + x] = ctr[x];
             }
+            if (t == 0) stamp(9);
             grid.sync();
+            if (t == 0) stamp(10);
             STRIDE_LOOP(j, F) {
                 float x = a.g[3 * j], y = a.g[3 * j + 1], z = a.g[3 * j + 2];
                 if (t == 0) { x -= a.g_last[3 * j]; y -= a.g_last[3 * j + 1]; z -= a.g_last[3 * j + 2]; }
@@ -354,8 +411,10 @@ dual_loss_kernel(const Args a) {
                 }
             }
         }
+        stamp(11);
         l4 = (float)(total(a.partials, 5, sm) / (double)F);
     }
+    stamp(12);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         const float l4s = l4 * a.bnf_scale;                      // `loss_norm2 * 0.0` while epoch <= 100 (main.py:101)
         a.losses[0] = l1; a.losses[1] = (double)l2; a.losses[2] = l3; a.losses[3] = (double)l4s; a.losses[4] = (double)l5;
@@ -392,8 +451,18 @@ extern "C" {
 
 int64_t ddmp_dual_loss_workspace_bytes(int64_t V, int64_t F, int32_t loop) {
     if (V <= 0 || F <= 0 || loop < 0) return 0;
-    const int64_t floats = 3 * V + 3 * F + F + 3 * F + (int64_t)(loop > 0 ? loop : 1) * 3 * F + 3 * F + 3 * F + 9 * F + 18 * F;
+    const int64_t floats = 4 + 4 * V + 12 * F + 3 * V + 3 * F + F + 3 * F + (int64_t)(loop > 0 ? loop : 1) * 3 * F + 3 * F + 3 * F + 18 * F;
     return ((floats * 4 + 15) / 16) * 16 + (int64_t)ddmp::fusedloss::kSlots * ddmp::fusedloss::kMaxBlocks * 8;
+}
+
+int ddmp_dual_loss_trace(uint64_t* out16) {
+    DDMP_REQUIRE(out16, "dual_loss_trace: null pointer");
+    cudaError_t e = cudaMemcpyFromSymbol(out16, ddmp::fusedloss::g_trace, 16 * sizeof(unsigned long long));
+    if (e != cudaSuccess) {
+        ddmp::set_error("dual_loss_trace: %s", cudaGetErrorString(e));
+        return DDMP_ERR_CUDA;
+    }
+    return DDMP_OK;
 }
 
 int ddmp_dual_loss(const float* pos, const float* nrm, const double* tgt_vs, const double* tgt_fn,
@@ -413,6 +482,9 @@ int ddmp_dual_loss(const float* pos, const float* nrm, const double* tgt_vs, con
     a.pos = pos; a.nrm = nrm; a.tgt_vs = tgt_vs; a.tgt_fn = tgt_fn; a.faces = faces; a.f2f = f2f; a.rslot = rslot;
     a.lap_rowptr = lap_rowptr; a.lap_col = lap_col; a.corner_ptr = corner_ptr; a.corner_slot = corner_slot;
     float* w = static_cast<float*>(workspace);
+    w += (4 - ((reinterpret_cast<uintptr_t>(w) / 4) & 3)) & 3;       // 16-byte records first
+    a.ds = w; w += 4 * V;
+    a.face_tmp = w; w += 12 * F;
     a.d = w; w += 3 * V;
     a.fc = w; w += 3 * F;
     a.fa = w; w += F;
@@ -420,7 +492,6 @@ int ddmp_dual_loss(const float* pos, const float* nrm, const double* tgt_vs, con
     a.normals = w; w += (int64_t)(loop > 0 ? loop : 1) * 3 * F;
     a.g_last = w; w += 3 * F;
     a.g = w; w += 3 * F;
-    a.face_tmp = w; w += 9 * F;
     a.msg = w; w += 18 * F;
     const int64_t off = (((w - static_cast<float*>(workspace)) * 4 + 15) / 16) * 16;
     a.partials = reinterpret_cast<double*>(static_cast<char*>(workspace) + off);

@@ -232,7 +232,8 @@ spmm_gcn_slice_kernel(const int* __restrict__ rowptr, const int* __restrict__ co
     const int64_t blk = blockIdx.x / slices;
     const int c0 = slice * CW;
     const float* __restrict__ Hs = H + c0 + lane * 4;
-    __shared__ __align__(16) float red[STATS ? GROUPS * 2 * CW : 4];
+    // 8 KB, not GROUPS * 2 * C floats: shared memory comes out of the L1 that serves the gathers (see the merge below)
+    __shared__ __align__(16) float red[STATS ? GROUPS * 2 * 128 : 4];
     __shared__ float wmax[8];
 
     const int64_t row0 = blk * rows_per_block;
@@ -334,33 +335,35 @@ spmm_gcn_slice_kernel(const int* __restrict__ rowptr, const int* __restrict__ co
         start = nstart; end = nend; myc = nmyc; myw = nmyw;
     }
     if (STATS) {
-        float* myred = red + gid * 2 * CW;
-#pragma unroll
-        for (int v = 0; v < NV; ++v) {
-            st4(myred + v * 128 + lane * 4, mean[v]);
-            st4(myred + CW + v * 128 + lane * 4, m2[v]);
-        }
-        __syncthreads();
-        // merge the 8 warps channel-wise in warp order (Chan et al.): block (sum, M2 about its mean)
+        // merge the 8 warps channel-wise in warp order (Chan et al.): block (sum, M2 about its mean); 128 channels per
+        // round through an 8 KB buffer
         float* outp = partials + blk * 2 * C + c0;
         const int rows_blk = (int)(row_end - row0);
-        if (threadIdx.x < CW) {
-            const int ch = threadIdx.x;
-            float n_a = 0.f, mu = 0.f, q = 0.f;
+        float* myred = red + gid * 2 * 128;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            st4(myred + lane * 4, mean[v]);
+            st4(myred + 128 + lane * 4, m2[v]);
+            __syncthreads();
+            if (threadIdx.x < 128) {
+                const int ch = threadIdx.x;
+                float n_a = 0.f, mu = 0.f, q = 0.f;
 #pragma unroll 4
-            for (int g = 0; g < GROUPS; ++g) {
-                if (g < rows_blk) {
-                    const float n_b = (float)((rows_blk - g + GROUPS - 1) / GROUPS);
-                    const float mb = red[g * 2 * CW + ch], qb = red[g * 2 * CW + CW + ch];
-                    const float nn = n_a + n_b;
-                    const float d = mb - mu;
-                    mu = fmaf(d, n_b / nn, mu);
-                    q += qb + d * d * (n_a * n_b / nn);
-                    n_a = nn;
+                for (int g = 0; g < GROUPS; ++g) {
+                    if (g < rows_blk) {
+                        const float n_b = (float)((rows_blk - g + GROUPS - 1) / GROUPS);
+                        const float mb = red[g * 256 + ch], qb = red[g * 256 + 128 + ch];
+                        const float nn = n_a + n_b;
+                        const float d = mb - mu;
+                        mu = fmaf(d, n_b / nn, mu);
+                        q += qb + d * d * (n_a * n_b / nn);
+                        n_a = nn;
+                    }
                 }
+                outp[v * 128 + ch] = mu * n_a;
+                outp[C + v * 128 + ch] = q;
             }
-            outp[ch] = mu * n_a;
-            outp[C + ch] = q;
+            __syncthreads();
         }
     }
     if (amax_blocks) {                               // one maximum per (row block, slice)
@@ -585,6 +588,11 @@ static int launch_spmm(const int* rowptr, const int* col, const float* w, const 
         }
 #undef DDMP_LAUNCH_SLICE
         return check_launch("spmm_gcn_slice");
+    }
+    static const int carve = [] { const char* e = getenv("DDMP_SPMM_CARVEOUT"); return e ? atoi(e) : -1; }();
+    if (carve >= 0) {       // experiment: how much of the gap between the flavours is the L1 the statistics buffer takes
+        cudaFuncSetAttribute(spmm_gcn_kernel<C, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        cudaFuncSetAttribute(spmm_gcn_kernel<C, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
     }
     if (partials) {
         if (bias) spmm_gcn_kernel<C, true, true><<<grid, 256, 0, st>>>(rowptr, col, w, H, bias, Y, partials, amax_blocks, n, rpb, bpc, fl);

@@ -315,6 +315,11 @@ int ddmp_dual_loss(const float* pos, const float* nrm, const double* tgt_vs, con
                    float k3, float k4, float k5, float bnf_scale, int32_t loop, void* workspace,
                    int64_t workspace_bytes, float* gpos, float* gnrm, double* losses, int64_t V, int64_t F,
                    void* stream);
+/* Phase trace of the most recent ddmp_dual_loss launch on the current device: 13 %globaltimer stamps (ns) taken by block
+ * 0 at the phase boundaries (start | P1 vertices | P1 faces | publish + barrier | totals | P2 vertices | P2 faces |
+ * publish + barrier | total + filter | publish + filter backward: messages | barrier | gather | final total),
+ * out16[13..15] unused (scripts/bench_loss.py prints the differences).  Synchronises the device. */
+int ddmp_dual_loss_trace(uint64_t* out16);
 
 /* mean angular distance in degrees between two sets of unit normals, float64 [ref: util/loss.py:261-272]. */
 int ddmp_mad(const float* n1, const float* n2, double* out, void* scratch, int64_t F, void* stream);
