@@ -113,11 +113,6 @@ int ddmp_rows_per_block(int32_t C) {
         static const int rpb64 = [] { const char* e = getenv("DDMP_RPB64"); return (e && atoi(e) == 256) ? 256 : 128; }();
         return rpb64;
     }
-    if (C >= 256) {                                  // A/B switch: DDMP_RPB_WIDE=64 halves the life of a wide-layer CTA
-        static const int rpbw = [] { const char* e = getenv("DDMP_RPB_WIDE"); const int v = e ? atoi(e) : 0;
-                                     return (v == 64 || v == 256) ? v : 128; }();
-        return rpbw;
-    }
     return C <= 32 ? 256 : 128;
 }
 

@@ -28,7 +28,6 @@ namespace tc {
 
 constexpr int kProducerWarps = 8;
 constexpr int kProducerThreads = kProducerWarps * 32;
-constexpr int kThreads = kProducerThreads + 32;      // + MMA warp
 constexpr int BM = 128;                              // UMMA M
 constexpr int BK = 32;                               // 32 fp32 = 128 bytes = one swizzle atom row
 constexpr int UMMA_K = 8;                            // kind::tf32
@@ -134,197 +133,6 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_mn_major,
 // byte offset of (row r, 16-byte chunk c) inside a K-major SWIZZLE_128B tile whose rows are 128 bytes
 __device__ __forceinline__ uint32_t sw128(uint32_t r, uint32_t c) { return r * 128u + ((c ^ (r & 7u)) << 4); }
 
-struct NtArgs {
-    const float* A;       // [*, K] row-major; row m of the tile is A[map ? map[m] : m]
-    const float* B;       // [N, K] row-major
-    float* C;             // [M, N]
-    const int* a_map;
-    const float* scale;   // act over k (A operand) when non-null
-    const float* shift;
-    float slope;
-    int64_t M;
-    int N, K;
-    int tiles_n;
-};
-
-// ---- NT kernel ------------------------------------------------------------------------------------------------------
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(kThreads, 1) tc_gemm_nt_kernel(const NtArgs g) {
-    constexpr uint32_t A_BYTES = BM * 128;           // one of hi / lo
-    constexpr uint32_t B_BYTES = BN * 128;
-    constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // carve: stages (1024-aligned), then barriers
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-    uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* accum_bar = empty_bar + STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tn = blockIdx.x % g.tiles_n;
-    const int64_t m0 = (int64_t)(blockIdx.x / g.tiles_n) * BM;
-    const int n0 = tn * BN;
-    const int num_kb = g.K / BK;
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) {
-            mbar_init(full_bar + s, kProducerWarps);
-            mbar_init(empty_bar + s, 1);
-        }
-        mbar_init(accum_bar, 1);
-        fence_barrier_init();
-    }
-    if (warp == kProducerWarps) tmem_alloc(tmem_slot, TMEM_COLS);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    const uint32_t smem_base = smem_u32(smem);
-
-    if (warp < kProducerWarps) {
-        // ===== producers: global -> (act, split) -> swizzled smem =====
-        const int t = threadIdx.x;               // 0..255
-        const uint32_t c = t & 7;                // 16-byte chunk along K owned by this thread
-        const bool has_act = g.scale != nullptr;
-        for (int kb = 0; kb < num_kb; ++kb) {
-            const int s = kb % STAGES;
-            const uint32_t ph = (kb / STAGES) & 1;
-            const int k0 = kb * BK + c * 4;
-            // issue the global loads before waiting for the slot
-            float4 av[BM * 8 / kProducerThreads];
-#pragma unroll
-            for (int j = 0; j < BM * 8 / kProducerThreads; ++j) {
-                const int row = (t >> 3) + j * (kProducerThreads / 8);
-                const int64_t m = m0 + row;
-                if (m < g.M) {
-                    const int64_t src = g.a_map ? (int64_t)__ldg(g.a_map + m) : m;
-                    av[j] = ldg4(g.A + src * g.K + k0);
-                } else {
-                    av[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-            }
-            float4 bv[BN * 8 / kProducerThreads];
-#pragma unroll
-            for (int j = 0; j < BN * 8 / kProducerThreads; ++j) {
-                const int row = (t >> 3) + j * (kProducerThreads / 8);
-                bv[j] = ldg4(g.B + (int64_t)(n0 + row) * g.K + k0);
-            }
-            float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (has_act) { sc = ldg4(g.scale + k0); sh = ldg4(g.shift + k0); }
-
-            mbar_wait(empty_bar + s, ph ^ 1u);
-            const uint32_t st = smem_base + s * STAGE_BYTES;
-#pragma unroll
-            for (int j = 0; j < BM * 8 / kProducerThreads; ++j) {
-                const uint32_t row = (t >> 3) + j * (kProducerThreads / 8);
-                float4 a = av[j];
-                if (has_act && (m0 + row) < g.M) {
-                    a.x = lrelu_max(fmaf(a.x, sc.x, sh.x), g.slope); a.y = lrelu_max(fmaf(a.y, sc.y, sh.y), g.slope);
-                    a.z = lrelu_max(fmaf(a.z, sc.z, sh.z), g.slope); a.w = lrelu_max(fmaf(a.w, sc.w, sh.w), g.slope);
-                }
-                uint4 hi, lo;
-                split_tf32(a.x, hi.x, lo.x); split_tf32(a.y, hi.y, lo.y);
-                split_tf32(a.z, hi.z, lo.z); split_tf32(a.w, hi.w, lo.w);
-                const uint32_t off = sw128(row, c);
-                sts128(st + off, hi);
-                sts128(st + A_BYTES + off, lo);
-            }
-#pragma unroll
-            for (int j = 0; j < BN * 8 / kProducerThreads; ++j) {
-                const uint32_t row = (t >> 3) + j * (kProducerThreads / 8);
-                const float4 b = bv[j];
-                uint4 hi, lo;
-                split_tf32(b.x, hi.x, lo.x); split_tf32(b.y, hi.y, lo.y);
-                split_tf32(b.z, hi.z, lo.z); split_tf32(b.w, hi.w, lo.w);
-                const uint32_t off = sw128(row, c);
-                sts128(st + 2 * A_BYTES + off, hi);
-                sts128(st + 2 * A_BYTES + B_BYTES + off, lo);
-            }
-            fence_proxy_async();                 // make the generic-proxy stores visible to the tensor-core proxy
-            __syncwarp();
-            if (lane == 0) mbar_arrive(full_bar + s);
-        }
-
-        // ===== epilogue: TMEM -> registers -> global =====
-        mbar_wait(accum_bar, 0);
-        tc_fence_after();
-        const int q = warp & 3;                  // TMEM lane quarter this warp may access
-        const int half = warp >> 2;              // column half
-        const int64_t m = m0 + q * 32 + lane;
-#pragma unroll 1
-        for (int cb = half * (BN / 2); cb < (half + 1) * (BN / 2); cb += 32) {
-            uint32_t v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, v);
-            if (m < g.M) {
-                float* dst = g.C + m * g.N + n0 + cb;
-#pragma unroll
-                for (int e = 0; e < 32; e += 4)
-                    st4(dst + e, make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]),
-                                             __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3])));
-            }
-        }
-        tc_fence_before();
-    } else {
-        // ===== MMA issuer (one thread) =====
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(BM, BN, false, false);
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(full_bar + s, ph);
-                tc_fence_after();
-                const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
-#pragma unroll
-                for (int ks = 0; ks < BK / UMMA_K; ++ks) {
-                    const uint32_t koff = ks * UMMA_K * 4;       // bytes along K inside the swizzle atom
-                    const uint64_t a_hi = make_desc(sa + koff, 16, 1024);
-                    const uint64_t a_lo = make_desc(sa + A_BYTES + koff, 16, 1024);
-                    const uint64_t b_hi = make_desc(sa + 2 * A_BYTES + koff, 16, 1024);
-                    const uint64_t b_lo = make_desc(sa + 2 * A_BYTES + B_BYTES + koff, 16, 1024);
-                    umma_tf32(tmem_base, a_lo, b_hi, idesc, (kb | ks) != 0);
-                    umma_tf32(tmem_base, a_hi, b_lo, idesc, 1);
-                    umma_tf32(tmem_base, a_hi, b_hi, idesc, 1);
-                }
-                umma_commit(empty_bar + s);      // frees the smem stage when these MMAs retire
-            }
-            umma_commit(accum_bar);              // accumulator complete
-        }
-        __syncwarp();
-    }
-    __syncthreads();
-    if (warp == kProducerWarps) {
-        tc_fence_after();
-        tmem_dealloc(tmem_base, TMEM_COLS);
-    }
-}
-
-template <int BN, int STAGES>
-static int launch_nt(const NtArgs& g, cudaStream_t st) {
-    constexpr size_t smem = (size_t)STAGES * (2 * BM * 128 + 2 * BN * 128) + 1024 + 256;
-    static PerDeviceOnce configured;
-    if (configured.need()) {
-        DDMP_CUDA(cudaFuncSetAttribute(tc_gemm_nt_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem));
-        configured.mark();
-    }
-    const int64_t tiles = ceil_div(g.M, BM) * g.tiles_n;
-    DDMP_REQUIRE(tiles < (1ll << 31), "tc gemm: too many tiles");
-    tc_gemm_nt_kernel<BN, STAGES><<<(unsigned)tiles, kThreads, smem, st>>>(g);
-    return check_launch("tc_gemm_nt");
-}
-
-static int run_nt(const float* A, const int* a_map, const float* scale, const float* shift, float slope,
-                  const float* B, float* C, int64_t M, int N, int K, cudaStream_t st) {
-    NtArgs g{};
-    g.A = A; g.B = B; g.C = C; g.a_map = a_map; g.scale = scale; g.shift = shift; g.slope = slope;
-    g.M = M; g.N = N; g.K = K;
-    if (N % 256 == 0) { g.tiles_n = N / 256; return launch_nt<256, 2>(g, st); }
-    if (N % 128 == 0) { g.tiles_n = N / 128; return launch_nt<128, 3>(g, st); }
-    g.tiles_n = N / 64;
-    return launch_nt<64, 4>(g, st);
-}
 
 // ---- NT kernel, version 2: persistent, B streamed by TMA bulk copies, epilogue overlapped ---------------------------
 // The weights (B operand) are split into hi/lo and laid out ONCE per call in the exact swizzled shared-memory image
@@ -2543,26 +2351,19 @@ static int launch_tn16x2(const Tn16Args& g, cudaStream_t st) {
     return check_launch("tc_gemm_tn16x2");
 }
 
-__global__ void transpose_kernel(const float* __restrict__ W, float* __restrict__ Wt, int rows, int cols) {
-    __shared__ float tile[32][33];
-    const int x = blockIdx.x * 32 + threadIdx.x, y0 = blockIdx.y * 32;
-    for (int j = threadIdx.y; j < 32; j += blockDim.y)
-        if (x < cols && y0 + j < rows) tile[j][threadIdx.x] = W[(int64_t)(y0 + j) * cols + x];
-    __syncthreads();
-    const int xt = blockIdx.y * 32 + threadIdx.x, yt0 = blockIdx.x * 32;
-    for (int j = threadIdx.y; j < 32; j += blockDim.y)
-        if (xt < rows && yt0 + j < cols) Wt[(int64_t)(yt0 + j) * rows + xt] = tile[threadIdx.x][j];
-}
-
 }  // namespace tc
 
 static inline bool tc_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// The REDUCTION width of the NT kernels may be as small as 32 (one k-block of the 3xTF32 kernel): the 32 -> 64 forward
+// transform and the dH.W product of the 64 -> 32 layer then run on the tensor cores (1M rows: 0.118 vs 0.195 ms, 0.105
+// vs 0.153 ms on the FFMA kernel).  The OUTPUT width of an NT kernel stays >= 64; the TN kernel with a 32-row M tile
+// (dH^T.X of the 64 -> 32 layer) measured SLOWER than FFMA (0.342 vs 0.297 ms: it pays for a whole 128-row tile).
 bool tc_supported_xw(int64_t n, int32_t Cin, int32_t Cout) {
-    return n > 0 && Cin >= 64 && Cout >= 64 && Cin % 32 == 0 && Cout % 64 == 0 && Cout <= 4096;
+    return n > 0 && Cin >= 32 && Cout >= 64 && Cin % 32 == 0 && Cout % 64 == 0 && Cout <= 4096;
 }
 bool tc_supported_dx(int64_t n, int32_t Cin, int32_t Cout) {
-    return n > 0 && Cin >= 64 && Cout >= 64 && Cout % 32 == 0 && Cin % 64 == 0 && Cin <= 4096;
+    return n > 0 && Cin >= 64 && Cout >= 32 && Cout % 32 == 0 && Cin % 64 == 0 && Cin <= 4096;
 }
 bool tc_supported_dw(int64_t n, int32_t Cin, int32_t Cout) {
     return n > 0 && Cin >= 64 && Cout >= 64 && Cin % 64 == 0 && Cout % 4 == 0 && Cin <= 4096 && Cout <= 4096;
@@ -2570,16 +2371,10 @@ bool tc_supported_dw(int64_t n, int32_t Cin, int32_t Cout) {
 
 int64_t tc_gemm_nt_workspace_bytes(int32_t Cin, int32_t Cout) { return 2ll * Cin * Cout * (int64_t)sizeof(float); }
 
-static bool use_v1() {
-    static const bool v = [] { const char* e = getenv("DDMP_TC_V1"); return e && e[0] == '1'; }();
-    return v;
-}
-
 int tc_gemm_xw(const float* X, const int32_t* row_map, const float* scale, const float* shift, float slope,
                const float* W, float* H, void* workspace, int64_t workspace_bytes, int64_t n, int32_t Cin,
                int32_t Cout, const float* amax, int64_t amax_len, cudaStream_t st) {
     DDMP_REQUIRE(tc_aligned16(X) && tc_aligned16(W) && tc_aligned16(H), "tc_gemm_xw: pointers must be 16-byte aligned");
-    if (use_v1()) return tc::run_nt(X, row_map, scale, shift, slope, W, H, n, Cout, Cin, st);
     DDMP_REQUIRE(workspace && tc_aligned16(workspace) && workspace_bytes >= tc_gemm_nt_workspace_bytes(Cin, Cout),
                  "tc_gemm_xw: workspace too small");
     if (amax && amax_len > 0 && Cin % tc::BK16 == 0 && tc::f16_split_enabled())
@@ -2593,14 +2388,6 @@ int tc_gemm_dx(const float* dH, const float* W, float* gX, void* workspace, int6
     DDMP_REQUIRE(tc_aligned16(dH) && tc_aligned16(W) && tc_aligned16(gX), "tc_gemm_dx: pointers must be 16-byte aligned");
     DDMP_REQUIRE(workspace && tc_aligned16(workspace) && workspace_bytes >= tc_gemm_nt_workspace_bytes(Cin, Cout),
                  "tc_gemm_dx: workspace too small");
-    if (use_v1()) {
-        float* wt = reinterpret_cast<float*>(workspace);
-        dim3 grid((unsigned)ceil_div(Cin, 32), (unsigned)ceil_div(Cout, 32));
-        tc::transpose_kernel<<<grid, dim3(32, 8), 0, st>>>(W, wt, Cout, Cin);
-        int rc = check_launch("tc transpose");
-        if (rc) return rc;
-        return tc::run_nt(dH, nullptr, nullptr, nullptr, 0.f, wt, gX, n, Cin, Cout, st);
-    }
     if (amax && amax_len > 0 && Cout % tc::BK16 == 0 && tc::f16_split_enabled())
         return tc::run_nt16(dH, nullptr, nullptr, nullptr, 0.f, W, 1, workspace, gX, n, Cin, Cout, amax, amax_len, st);
     return tc::run_nt2(dH, nullptr, nullptr, nullptr, 0.f, W, 1, workspace, gX, n, Cin, Cout, st);

@@ -37,6 +37,9 @@ spmm_gcn_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, con
     }
     // BatchNorm partial sums live in shared memory, one private [2][C] slice per row group (keeping them in
     // registers costs 8*NV registers and halves the occupancy of the widest instantiation: ncu, profiles/)
+    // What this buffer costs is L1, not instructions: forcing a shared-memory carve-out on the PLAIN flavour slows it
+    // from 0.474 to 0.635 ms (vertex graph, C = 512), past the statistics flavour (0.591); with the moments in registers
+    // (256-channel slices) the time does not change (profiles/spmm_slice_ab_r2.txt).
     __shared__ __align__(16) float red[STATS ? GROUPS * 2 * C : 4];
     __shared__ float wmax[8];
     float* myred = red + gid * 2 * C;
@@ -202,182 +205,6 @@ spmm_gcn_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, con
         __syncthreads();
     }
     }   // row blocks of this CTA
-}
-
-// Channel-SLICED variant for the wide layers (C = 256 / 512): a CTA owns a CW-channel slice (CW = 128 or 256) of its
-// row block; grid.x = slices x row blocks, slice fastest, so the CTAs of one row block run side by side and share the
-// block's index stream in L2.  Two things the whole-row kernel above cannot do:
-//  * a warp keeps only CW/128 float4 accumulators per lane, which leaves room for the Welford state (mean, M2) of the
-//    BatchNorm epilogue IN REGISTERS.  The kernel above has none left at C = 512 and walks the state through shared
-//    memory on every row (2 x LDS.128 + 2 x STS.128 per float4 and row, +70 % instructions: 0.94 vs 0.78 ms against the
-//    plain flavour on the 1M-face graph, ncu profiles/ncu_full_r2_summary.txt);
-//  * a CTA lives CW/C as long.  At 6 TB/s the 126 MB L2 turns over every ~20-40 us while a 128-row x 2 KB block lives
-//    ~44 us, so about half of the 15-18 % references that leave the row block miss L2 although the neighbouring block
-//    fetched the same row moments earlier (ncu: DRAM reads 26 % / 42 % above the algorithmic bytes on the face / vertex
-//    graph at C = 512, with only 0.3 % of the references further than one wave of CTAs away).  Shorter-lived CTAs
-//    shrink the time between the two uses of a row.
-// Same warp -> row assignment, the same per-element accumulation order and the same Chan merge as the kernel above:
-// Y, the block moments and max|Y| are bitwise identical (tests/test_gpu_ops.py).
-template <int CW, bool STATS, bool BIAS>
-__global__ void __launch_bounds__(256, (CW == 128 && !STATS) ? 4 : 3)
-spmm_gcn_slice_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const float* __restrict__ w,
-                      const float* __restrict__ H, const float* __restrict__ bias, float* __restrict__ Y,
-                      float* __restrict__ partials, float* __restrict__ amax_blocks, int64_t n, int rows_per_block,
-                      int C, int slices) {
-    constexpr int NV = CW / 128;            // float4 per lane
-    constexpr int GROUPS = 8;
-    const int lane = threadIdx.x & 31;
-    const int gid = threadIdx.x >> 5;
-    const int slice = blockIdx.x % slices;
-    const int64_t blk = blockIdx.x / slices;
-    const int c0 = slice * CW;
-    const float* __restrict__ Hs = H + c0 + lane * 4;
-    // 8 KB, not GROUPS * 2 * C floats: shared memory comes out of the L1 that serves the gathers (see the merge below)
-    __shared__ __align__(16) float red[STATS ? GROUPS * 2 * 128 : 4];
-    __shared__ float wmax[8];
-
-    const int64_t row0 = blk * rows_per_block;
-    const int64_t row_end = (row0 + rows_per_block < n) ? (row0 + rows_per_block) : n;
-    float4 mean[STATS ? NV : 1], m2[STATS ? NV : 1];
-    if (STATS) {
-#pragma unroll
-        for (int v = 0; v < NV; ++v) mean[v] = m2[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    float wcnt = 0.f, amx = 0.f;
-
-    int64_t r = row0 + gid;
-    int start = 0, end = 0, myc = 0;
-    float myw = 0.f;
-    if (r < row_end) {
-        start = __ldg(rowptr + r);
-        end = __ldg(rowptr + r + 1);
-        const int kk = start + lane;
-        if (kk < end) { myc = __ldg(col + kk); myw = __ldg(w + kk); }
-    }
-    for (; r < row_end; r += GROUPS) {
-        const int64_t rn = r + GROUPS;
-        int nstart = 0, nend = 0, nmyc = 0;
-        float nmyw = 0.f;
-        if (rn < row_end) {
-            nstart = __ldg(rowptr + rn);
-            nend = __ldg(rowptr + rn + 1);
-        }
-        float4 acc[NV];
-#pragma unroll
-        for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-        bool prefetched = false;
-        // B gathered rows in flight, folded into the accumulators in CSR order
-#define DDMP_SLICE_BATCH(B)                                                                          \
-        {                                                                                            \
-            int cj[B];                                                                               \
-            float wj[B];                                                                             \
-            float4 x[B][NV];                                                                         \
-            _Pragma("unroll") for (int u = 0; u < B; ++u) {                                          \
-                cj[u] = __shfl_sync(0xffffffffu, myc, j + u);                                        \
-                wj[u] = __shfl_sync(0xffffffffu, myw, j + u);                                        \
-            }                                                                                        \
-            _Pragma("unroll") for (int u = 0; u < B; ++u) {                                          \
-                const float* hp = Hs + (int64_t)cj[u] * C;                                           \
-                _Pragma("unroll") for (int v = 0; v < NV; ++v) x[u][v] = ldg4(hp + v * 128);         \
-            }                                                                                        \
-            if (!prefetched && rn < row_end) { /* next row's first chunk, behind the gathers in flight */ \
-                const int kk = nstart + lane;                                                        \
-                if (kk < nend) { nmyc = __ldg(col + kk); nmyw = __ldg(w + kk); }                     \
-                prefetched = true;                                                                   \
-            }                                                                                        \
-            _Pragma("unroll") for (int u = 0; u < B; ++u) {                                          \
-                _Pragma("unroll") for (int v = 0; v < NV; ++v) {                                     \
-                    acc[v].x = fmaf(wj[u], x[u][v].x, acc[v].x);                                     \
-                    acc[v].y = fmaf(wj[u], x[u][v].y, acc[v].y);                                     \
-                    acc[v].z = fmaf(wj[u], x[u][v].z, acc[v].z);                                     \
-                    acc[v].w = fmaf(wj[u], x[u][v].w, acc[v].w);                                     \
-                }                                                                                    \
-            }                                                                                        \
-            j += B;                                                                                  \
-        }
-        for (int k0 = start; k0 < end; k0 += 32) {
-            if (k0 != start) {
-                const int kk = k0 + lane;
-                myc = (kk < end) ? __ldg(col + kk) : 0;
-                myw = (kk < end) ? __ldg(w + kk) : 0.f;
-            }
-            const int cnt = (end - k0 < 32) ? (end - k0) : 32;
-            int j = 0;
-            while (j + 4 <= cnt) DDMP_SLICE_BATCH(4)
-            if (j + 2 <= cnt) DDMP_SLICE_BATCH(2)
-            if (j < cnt) DDMP_SLICE_BATCH(1)
-        }
-#undef DDMP_SLICE_BATCH
-        if (!prefetched && rn < row_end) {           // empty row (cannot happen with self loops): keep the pipeline fed
-            const int kk = nstart + lane;
-            if (kk < nend) { nmyc = __ldg(col + kk); nmyw = __ldg(w + kk); }
-        }
-        float* yp = Y + r * C + c0 + lane * 4;
-        wcnt += 1.f;
-        const float winv = 1.f / wcnt;
-#pragma unroll
-        for (int v = 0; v < NV; ++v) {
-            float4 o = acc[v];
-            if (BIAS) {
-                const float4 b = ldg4(bias + c0 + v * 128 + lane * 4);       // L1-resident; not worth 4*NV registers
-                o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-            }
-            __stcs(reinterpret_cast<float4*>(yp + v * 128), o);
-            if (amax_blocks) amx = fmaxf(fmaxf(amx, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
-            if (STATS) {                             // Welford: running mean and M2 of this warp's rows (see bn.cu)
-                float d;
-                d = o.x - mean[v].x; mean[v].x = fmaf(d, winv, mean[v].x); m2[v].x = fmaf(d, o.x - mean[v].x, m2[v].x);
-                d = o.y - mean[v].y; mean[v].y = fmaf(d, winv, mean[v].y); m2[v].y = fmaf(d, o.y - mean[v].y, m2[v].y);
-                d = o.z - mean[v].z; mean[v].z = fmaf(d, winv, mean[v].z); m2[v].z = fmaf(d, o.z - mean[v].z, m2[v].z);
-                d = o.w - mean[v].w; mean[v].w = fmaf(d, winv, mean[v].w); m2[v].w = fmaf(d, o.w - mean[v].w, m2[v].w);
-            }
-        }
-        start = nstart; end = nend; myc = nmyc; myw = nmyw;
-    }
-    if (STATS) {
-        // merge the 8 warps channel-wise in warp order (Chan et al.): block (sum, M2 about its mean); 128 channels per
-        // round through an 8 KB buffer
-        float* outp = partials + blk * 2 * C + c0;
-        const int rows_blk = (int)(row_end - row0);
-        float* myred = red + gid * 2 * 128;
-#pragma unroll
-        for (int v = 0; v < NV; ++v) {
-            st4(myred + lane * 4, mean[v]);
-            st4(myred + 128 + lane * 4, m2[v]);
-            __syncthreads();
-            if (threadIdx.x < 128) {
-                const int ch = threadIdx.x;
-                float n_a = 0.f, mu = 0.f, q = 0.f;
-#pragma unroll 4
-                for (int g = 0; g < GROUPS; ++g) {
-                    if (g < rows_blk) {
-                        const float n_b = (float)((rows_blk - g + GROUPS - 1) / GROUPS);
-                        const float mb = red[g * 256 + ch], qb = red[g * 256 + 128 + ch];
-                        const float nn = n_a + n_b;
-                        const float d = mb - mu;
-                        mu = fmaf(d, n_b / nn, mu);
-                        q += qb + d * d * (n_a * n_b / nn);
-                        n_a = nn;
-                    }
-                }
-                outp[v * 128 + ch] = mu * n_a;
-                outp[C + v * 128 + ch] = q;
-            }
-            __syncthreads();
-        }
-    }
-    if (amax_blocks) {                               // one maximum per (row block, slice)
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) amx = fmaxf(amx, __shfl_xor_sync(0xffffffffu, amx, o));
-        if (lane == 0) wmax[gid] = amx;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            float m = wmax[0];
-#pragma unroll
-            for (int i = 1; i < 8; ++i) m = fmaxf(m, wmax[i]);
-            amax_blocks[blockIdx.x] = m;
-        }
-    }
 }
 
 // Backward aggregation fused with the BatchNorm/LeakyReLU backward "apply":
@@ -546,19 +373,6 @@ __global__ void gcn_edge_weights_kernel(const int* __restrict__ rowptr, const in
     }
 }
 
-// Slice width of the channel-sliced kernel for this width and flavour, 0 = whole-row kernel.  flags (setting >> 4 of
-// ddmp_spmm_use_tile_kernel): 4 / 8 = 256- / 128-channel slices for the statistics (forward) flavour, 16 / 32 = the
-// same for the plain (backward) flavour.
-int spmm_slice_width(int C, bool stats) {
-    if (C != 256 && C != 512) return 0;
-    static const bool chunked = [] { const char* e = getenv("DDMP_SPMM_CHUNK"); return e && atoi(e) > 1; }();
-    if (chunked) return 0;
-    const int fl = spmm_flags() >> (stats ? 2 : 4);
-    if (fl & 2) return 128;
-    if (fl & 1) return 256;
-    return 0;
-}
-
 template <int C>
 static int launch_spmm(const int* rowptr, const int* col, const float* w, const float* H, const float* bias,
                        float* Y, float* partials, float* amax_blocks, int64_t n, cudaStream_t st) {
@@ -572,28 +386,6 @@ static int launch_spmm(const int* rowptr, const int* col, const float* w, const 
     while (bpc > 1 && ceil_div(nblk, bpc) < 8 * kNumSMs) --bpc;
     const unsigned grid = (unsigned)ceil_div(nblk, bpc);
     const int fl = spmm_flags();
-    // max|Y| is laid out per (row block, slice) of the PLAIN flavour (ddmp_spmm_amax_len), whoever asks for it
-    const int cw = spmm_slice_width(C, partials != nullptr && amax_blocks == nullptr);
-    if (cw) {
-        const int slices = C / cw;
-        const unsigned g2 = (unsigned)(nblk * slices);
-#define DDMP_LAUNCH_SLICE(CW, S, B) \
-        spmm_gcn_slice_kernel<CW, S, B><<<g2, 256, 0, st>>>(rowptr, col, w, H, bias, Y, partials, amax_blocks, n, rpb, C, slices)
-        if (cw == 256) {
-            if (partials) { if (bias) DDMP_LAUNCH_SLICE(256, true, true); else DDMP_LAUNCH_SLICE(256, true, false); }
-            else { if (bias) DDMP_LAUNCH_SLICE(256, false, true); else DDMP_LAUNCH_SLICE(256, false, false); }
-        } else {
-            if (partials) { if (bias) DDMP_LAUNCH_SLICE(128, true, true); else DDMP_LAUNCH_SLICE(128, true, false); }
-            else { if (bias) DDMP_LAUNCH_SLICE(128, false, true); else DDMP_LAUNCH_SLICE(128, false, false); }
-        }
-#undef DDMP_LAUNCH_SLICE
-        return check_launch("spmm_gcn_slice");
-    }
-    static const int carve = [] { const char* e = getenv("DDMP_SPMM_CARVEOUT"); return e ? atoi(e) : -1; }();
-    if (carve >= 0) {       // experiment: how much of the gap between the flavours is the L1 the statistics buffer takes
-        cudaFuncSetAttribute(spmm_gcn_kernel<C, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-        cudaFuncSetAttribute(spmm_gcn_kernel<C, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-    }
     if (partials) {
         if (bias) spmm_gcn_kernel<C, true, true><<<grid, 256, 0, st>>>(rowptr, col, w, H, bias, Y, partials, amax_blocks, n, rpb, bpc, fl);
         else spmm_gcn_kernel<C, true, false><<<grid, 256, 0, st>>>(rowptr, col, w, H, bias, Y, partials, amax_blocks, n, rpb, bpc, fl);
@@ -667,9 +459,7 @@ int ddmp_spmm_use_tile_kernel(int mode) { return ddmp::spmm_tile_set(mode); }
 
 int64_t ddmp_spmm_amax_len(int64_t n, int32_t C) {
     const int64_t nblk = ddmp_num_row_blocks(n, C);
-    if (ddmp::spmm_tile_supported(n, C)) return C > 128 ? nblk * (C / 128) : nblk;
-    const int cw = ddmp::spmm_slice_width(C, false);      // channel-sliced kernel: one maximum per (row block, slice)
-    return cw ? nblk * (C / cw) : nblk;
+    return ddmp::spmm_tile_supported(n, C) && C > 128 ? nblk * (C / 128) : nblk;
 }
 
 int ddmp_spmm_bn_bwd(const int32_t* rowptr, const int32_t* col, const float* w, const float* gX, const float* Y,

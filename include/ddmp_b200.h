@@ -77,10 +77,7 @@ int64_t ddmp_spmm_amax_len(int64_t n, int32_t C);
 /* Kernel choice of ddmp_spmm_gcn (environment DDMP_SPMM_TILE, default 33).  setting = mode | flags << 4.
  * mode: 0 = gather-only kernel for every width, 1 = tile-staged kernel for C <= 128 (where it measures faster on B200),
  * 2 = tile-staged kernel for every mesh width (A/B measurements, bit-exactness test between the two kernels).
- * flags: 2 = streaming stores of Y in the gather kernel; 4 / 8 = channel-sliced kernel (a CTA owns a 256- / 128-channel
- * slice of its row block, BatchNorm moments in registers) for the statistics flavour at C = 256, 512; 16 / 32 = the same
- * for the plain flavour (amax_blocks then holds one maximum per (row block, slice): ddmp_spmm_amax_len).  Results are
- * bitwise independent of the setting.  Returns the previous setting. */
+ * flags: bit 1 = streaming stores of Y in the gather kernel.  Returns the previous setting. */
 int ddmp_spmm_use_tile_kernel(int mode);
 
 /* Backward aggregation fused with ddmp_bn_bwd_apply:  dH = A_hat * dY  with dY recomputed on the fly from the gathered

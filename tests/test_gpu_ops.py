@@ -384,6 +384,35 @@ def test_gemm_tcgen05_3xtf32(cin, cout, n):
     assert rel_err(a, F_.gemm_xw(Xn, Wd, scale=sc, shift=sh, backend=1)) < 1e-5
 
 
+@pytest.mark.parametrize("n", [640, 1000, 4099, 20011])
+def test_gemm_tcgen05_narrow_reduction_width(n):
+    """32-wide reductions on the tensor-core kernels: X.W^T of the 32 -> 64 layer and dH.W of the 64 -> 32 layer (K = 32:
+    one k-block of the 3xTF32 kernel) against float64, the FFMA kernel, and through the default dispatch"""
+    from dual_dmp_b200 import functional as F_
+    torch.manual_seed(n)
+    X = torch.randn(n, 32); W = torch.randn(64, 32) / 32 ** 0.5
+    scale, shift = torch.rand(32) + 0.5, torch.randn(32)
+    act = torch.nn.functional.leaky_relu(X.double() * scale.double() + shift.double(), 0.01)
+    Xd, Wd, sc, sh = X.to(DEV), W.to(DEV), scale.to(DEV), shift.to(DEV)
+    e1 = rel_err(F_.gemm_xw(Xd, Wd, backend=2), X.double() @ W.double().t())
+    a = F_.gemm_xw(Xd, Wd, scale=sc, shift=sh, backend=2)
+    e2 = rel_err(a, act @ W.double().t())
+    assert torch.equal(a, F_.gemm_xw(Xd, Wd, scale=sc, shift=sh)), "default dispatch must take the tensor-core kernel"
+    assert rel_err(a, F_.gemm_xw(Xd, Wd, scale=sc, shift=sh, backend=1)) < 1e-5
+    # 64 -> 32 layer
+    X2 = torch.randn(n, 64); W2 = torch.randn(32, 64) / 8; dH = torch.randn(n, 32)
+    sc2, sh2 = torch.rand(64) + 0.5, torch.randn(64)
+    act2 = torch.nn.functional.leaky_relu(X2.double() * sc2.double() + sh2.double(), 0.01)
+    X2d, W2d, dHd, sc2d, sh2d = X2.to(DEV), W2.to(DEV), dH.to(DEV), sc2.to(DEV), sh2.to(DEV)
+    g = F_.gemm_dx(dHd, W2d, backend=2)
+    e3 = rel_err(g, dH.double() @ W2.double())
+    assert torch.equal(g, F_.gemm_dx(dHd, W2d))
+    d = F_.gemm_dw(dHd, X2d, 64, scale=sc2d, shift=sh2d)          # stays on the FFMA kernel (measured faster)
+    e4 = rel_err(d, dH.double().t() @ act2)
+    report(f"gemm_tc narrow n={n}", (e1, e2, e3, e4))
+    assert max(e1, e2, e3) < 1e-5 and e4 < 2e-5, (e1, e2, e3, e4)
+
+
 @pytest.mark.parametrize("cin,cout", TC_SHAPES)
 @pytest.mark.parametrize("n", [640, 4099, 20011])
 def test_gemm_tcgen05_f16_split(cin, cout, n):
@@ -526,50 +555,6 @@ def test_spmm_tile_kernel_equals_gather_kernel_bitwise(kind, n, C):
                 outs.append(F_.spmm_gcn(sub, H, bias=b, n_rows=n_own))
             assert outs[0].shape == (n_own, C) and torch.equal(outs[0], outs[1])
             assert torch.equal(outs[0], res[0][0][:n_own])
-    finally:
-        lib.query("ddmp_spmm_use_tile_kernel", prev)
-
-
-@pytest.mark.parametrize("C", [256, 512])
-@pytest.mark.parametrize("kind,n", [("ico", 3), ("open", 9), ("ico", 40)])
-def test_spmm_channel_sliced_kernel_equals_whole_row_kernel_bitwise(kind, n, C):
-    """spmm_gcn_slice_kernel (wide layers: a CTA owns a 128- or 256-channel slice of its row block, Welford state of the
-    BatchNorm epilogue in registers; flags 4 / 8 / 16 / 32 of ddmp_spmm_use_tile_kernel) walks the rows of a block with
-    the same warp -> row assignment, the same per-element accumulation order and the same Chan merge as
-    spmm_gcn_kernel, so Y, the (sum, M2) block partials and max|Y| must be IDENTICAL -- both flavours, with and without
-    bias, ragged last block, partitioned layout ([owned | halo] rows)."""
-    from dual_dmp_b200 import functional as F_
-    from dual_dmp_b200._lib import lib
-    from dual_dmp_b200.graph import GcnGraph
-    from oracle.step_ref import make_dataset
-    n_mesh, s_mesh, _ = small_case(kind, n)
-    ds = make_dataset(n_mesh, s_mesh)
-    V, F = len(n_mesh.vs), len(n_mesh.faces)
-    graphs_ = [GcnGraph(ds.edge_index, V, DEV, coords=ds.x_pos, reorder=True),
-               GcnGraph(ds.face_index, F, DEV, coords=ds.z2.detach()[:, :3], reorder=True)]
-    torch.manual_seed(C + n)
-    prev = lib.query("ddmp_spmm_use_tile_kernel", 0)
-    try:
-        for graph in graphs_:
-            H = torch.randn(graph.n, C, device=DEV)
-            b = torch.randn(C, device=DEV) * 3
-            n_own = graph.n - max(1, graph.n // 7)
-            rp = graph.rowptr[: n_own + 1].contiguous()
-            sub = type("G", (), dict(rowptr=rp, col=graph.col, w=graph.w, rowptr_t=rp, col_t=graph.col, w_t=graph.w))
-            res = {}
-            for flags in (0, 2, 4, 8, 16, 32, 2 | 4 | 16, 2 | 8 | 32, 4 | 32):
-                lib.query("ddmp_spmm_use_tile_kernel", 1 | (flags << 4))
-                Ya, Pa = F_.spmm_gcn(graph, H, bias=b, stats=True)
-                Yb, Pb = F_.spmm_gcn(graph, H, stats=True)
-                Yc, Pc = F_.spmm_gcn(sub, H, bias=b, stats=True, n_rows=n_own)
-                Yd, ab = F_.spmm_gcn(graph, H, amax=True)
-                Ye, Pe, ab2 = F_.spmm_gcn(graph, H, bias=b, stats=True, amax=True)
-                Yf = F_.spmm_gcn(sub, H, n_rows=n_own)
-                res[flags] = (Ya, Pa, Yb, Pb, Yc, Pc, Yd, ab.max(), Ye, Pe, ab2.max(), Yf)
-            assert float(res[0][7]) == float(res[0][6].abs().max())
-            for flags in list(res)[1:]:
-                for i, (x, x0) in enumerate(zip(res[flags], res[0])):
-                    assert torch.equal(x, x0), (flags, i, graph.n, C)
     finally:
         lib.query("ddmp_spmm_use_tile_kernel", prev)
 
