@@ -248,6 +248,38 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partials, float* 
     out[i] = s;
 }
 
+// The same sum for SMALL outputs (narrow layers: 64 ... 2,048 numbers, ~600 partials): the kernel above would run 1-8 CTAs
+// whose threads each walk the ~600 partials in one dependent chain (~70 us -- most of what ddmp_gemm_dw took on the narrow
+// layers).  Here a CTA owns 32 outputs, 8 z-lanes per output add every 8th partial in ascending order (independent
+// loads), and the 8 lane sums are folded in lane order: fixed order, deterministic.
+__global__ void __launch_bounds__(256)
+splitk_reduce_small_kernel(const float* __restrict__ partials, float* __restrict__ out, int64_t count, int splits) {
+    __shared__ float red[8][33];
+    const int o = threadIdx.x & 31, zl = threadIdx.x >> 5;
+    const int64_t i = (int64_t)blockIdx.x * 32 + o;
+    float s = 0.f;
+    if (i < count) {
+#pragma unroll 4
+        for (int z = zl; z < splits; z += 8) s += __ldg(partials + (int64_t)z * count + i);
+    }
+    red[zl][o] = s;
+    __syncthreads();
+    if (zl == 0 && i < count) {
+        float v = red[0][o];
+#pragma unroll
+        for (int z = 1; z < 8; ++z) v += red[z][o];
+        out[i] = v;
+    }
+}
+
+static int launch_splitk_reduce(const float* partials, float* out, int64_t count, int splits, cudaStream_t st) {
+    if (count <= 16384 && splits >= 32)
+        splitk_reduce_small_kernel<<<(unsigned)ceil_div(count, 32), 256, 0, st>>>(partials, out, count, splits);
+    else
+        splitk_reduce_kernel<<<(unsigned)ceil_div(count, 256), 256, 0, st>>>(partials, out, count, splits);
+    return check_launch("splitk_reduce");
+}
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 template <int BM, int BN, int TM, int TN, bool A_KC, bool B_KC, bool ACT_A, bool ACT_B>
@@ -299,6 +331,162 @@ int ffma_gemm_dx(const float* dH, const float* W, float* gX, int64_t n, int32_t 
     return launch_by_shape<true, false, false, false>(g, 1, vec, st);
 }
 
+// ---- dW of the narrow layers (both widths <= 64) --------------------------------------------------------------------
+// dW[M = Cout, N = Cin] = sum over rows of dH[r, :]^T * act(X)[r, :] is a reduction over ~1M rows into at most 64 x 64
+// numbers.  The general kernel above gives every output a thread of ONE tile: at 16 x 32 outputs that is a 64-thread CTA
+// (4.4 TFLOP/s, 0.23 ms for 0.19 GB of operands at 1M rows), at 32 x 64 half of a 64 x 64 tile idles.  Here a CTA of 256
+// threads always works: G = (M/4)(N/4) threads hold the output in 4 x 4 register tiles and the remaining factor
+// KG = 256 / G splits the ROWS of a stage between KG such groups (split-K inside the CTA, groups folded in group order
+// through shared memory at the end).  Stages of RS rows are staged through shared memory (coalesced float4 loads, the
+// BatchNorm + LeakyReLU of the X operand applied once per element on the way, double-buffered through registers), so the
+// inner loop is 2 LDS.128 + 16 FFMA per row and thread.  One partial per CTA, summed in CTA order by splitk_reduce_kernel.
+// rows per stage: the largest power of two whose two stage buffers fit DDMP_DWN_STAGE_BYTES (12 KB per stage: 64 rows at
+// 32 x 16, 32 at 64 x 32).  24 KB stages need 80-89 registers (3 CTAs per SM) or spill at 64 and measured the same
+// (scripts/bench_gemm_small.py: 0.073-0.186 vs 0.077-0.176 ms); what is left at 16 x 32 outputs is the one-stage-deep
+// pipeline (latency per stage), at 64 x 32 the FFMA issue rate (~40 % of peak).
+#ifndef DDMP_DWN_STAGE_BYTES
+#define DDMP_DWN_STAGE_BYTES 12288
+#endif
+constexpr int dw_narrow_stage_rows(int M, int N, int KG) {
+    int rs = 32;
+    while (2 * rs * (M + N) * 4 <= DDMP_DWN_STAGE_BYTES) rs *= 2;
+    return rs > KG ? rs : KG;
+}
+template <int M, int N>
+__global__ void __launch_bounds__(256, 4)     // 4 CTAs per SM = the 592 splits of dw_plan in one wave
+dw_narrow_kernel(const float* __restrict__ dH, const float* __restrict__ X, const int* __restrict__ x_map,
+                 const float* __restrict__ scale, const float* __restrict__ shift, float slope,
+                 float* __restrict__ partials, int64_t n, int64_t rows_per_cta) {
+    constexpr int G = (M / 4) * (N / 4);
+    constexpr int KG = 256 / G;
+    constexpr int RS = dw_narrow_stage_rows(M, N, KG);    // rows per stage
+    constexpr int A_F4 = RS * M / 4, B_F4 = RS * N / 4;   // float4 per stage
+    constexpr int A_V = (A_F4 + 255) / 256, B_V = (B_F4 + 255) / 256;
+    static_assert(256 % G == 0 && RS % KG == 0, "thread layout");
+    static_assert(256 % (M / 4) == 0 && 256 % (N / 4) == 0, "a thread stages a fixed channel quad");
+    constexpr int STAGE = RS * (M + N);
+    constexpr int RED = 256 * 16;
+    __shared__ __align__(16) float sm[(2 * STAGE > RED) ? 2 * STAGE : RED];
+    const int t = threadIdx.x;
+    const int kg = t / G, gi = t % G;
+    const int tm = gi / (N / 4), tn = gi % (N / 4);
+    const int64_t r_begin = (int64_t)blockIdx.x * rows_per_cta;
+    const int64_t r_end = (r_begin + rows_per_cta < n) ? (r_begin + rows_per_cta) : n;
+
+    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool has_act = scale != nullptr;
+    if (has_act) { sc = ldg4(scale + (t % (N / 4)) * 4); sh = ldg4(shift + (t % (N / 4)) * 4); }
+    float4 ra[A_V], rb[B_V];
+    auto load_stage = [&](int64_t r0) {
+#pragma unroll
+        for (int i = 0; i < A_V; ++i) {
+            const int idx = t + i * 256;
+            const int64_t r = r0 + idx / (M / 4);
+            ra[i] = (idx < A_F4 && r < r_end) ? ldg4(dH + r * M + (idx % (M / 4)) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < B_V; ++i) {
+            const int idx = t + i * 256;
+            const int64_t r = r0 + idx / (N / 4);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (idx < B_F4 && r < r_end) {
+                const int64_t src = x_map ? (int64_t)__ldg(x_map + r) : r;
+                v = ldg4(X + src * N + (idx % (N / 4)) * 4);
+                if (has_act) {
+                    float z;
+                    z = fmaf(v.x, sc.x, sh.x); v.x = z > 0.f ? z : z * slope;
+                    z = fmaf(v.y, sc.y, sh.y); v.y = z > 0.f ? z : z * slope;
+                    z = fmaf(v.z, sc.z, sh.z); v.z = z > 0.f ? z : z * slope;
+                    z = fmaf(v.w, sc.w, sh.w); v.w = z > 0.f ? z : z * slope;
+                }
+            }
+            rb[i] = v;
+        }
+    };
+    auto store_stage = [&](int buf) {
+        float* As = sm + buf * STAGE;
+        float* Bs = As + RS * M;
+#pragma unroll
+        for (int i = 0; i < A_V; ++i) {
+            const int idx = t + i * 256;
+            if (idx < A_F4) st4(As + idx * 4, ra[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < B_V; ++i) {
+            const int idx = t + i * 256;
+            if (idx < B_F4) st4(Bs + idx * 4, rb[i]);
+        }
+    };
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    const int64_t ns = (r_end > r_begin) ? ((r_end - r_begin + RS - 1) / RS) : 0;
+    if (ns > 0) {
+        load_stage(r_begin);
+        store_stage(0);
+    }
+    __syncthreads();
+    for (int64_t s = 0; s < ns; ++s) {
+        const int buf = (int)(s & 1);
+        if (s + 1 < ns) load_stage(r_begin + (s + 1) * RS);
+        const float* As = sm + buf * STAGE;
+        const float* Bs = As + RS * M;
+#pragma unroll 4
+        for (int k = kg; k < RS; k += KG) {
+            const float4 a = *reinterpret_cast<const float4*>(As + k * M + tm * 4);
+            const float4 b = *reinterpret_cast<const float4*>(Bs + k * N + tn * 4);
+            acc[0][0] = fmaf(a.x, b.x, acc[0][0]); acc[0][1] = fmaf(a.x, b.y, acc[0][1]);
+            acc[0][2] = fmaf(a.x, b.z, acc[0][2]); acc[0][3] = fmaf(a.x, b.w, acc[0][3]);
+            acc[1][0] = fmaf(a.y, b.x, acc[1][0]); acc[1][1] = fmaf(a.y, b.y, acc[1][1]);
+            acc[1][2] = fmaf(a.y, b.z, acc[1][2]); acc[1][3] = fmaf(a.y, b.w, acc[1][3]);
+            acc[2][0] = fmaf(a.z, b.x, acc[2][0]); acc[2][1] = fmaf(a.z, b.y, acc[2][1]);
+            acc[2][2] = fmaf(a.z, b.z, acc[2][2]); acc[2][3] = fmaf(a.z, b.w, acc[2][3]);
+            acc[3][0] = fmaf(a.w, b.x, acc[3][0]); acc[3][1] = fmaf(a.w, b.y, acc[3][1]);
+            acc[3][2] = fmaf(a.w, b.z, acc[3][2]); acc[3][3] = fmaf(a.w, b.w, acc[3][3]);
+        }
+        if (s + 1 < ns) store_stage(buf ^ 1);
+        __syncthreads();
+    }
+    // fold the KG row groups in group order: red[kg][m][n]
+    float* red = sm;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        st4(red + (kg * M + tm * 4 + i) * N + tn * 4, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
+    __syncthreads();
+    float* outp = partials + (int64_t)blockIdx.x * M * N;
+    for (int i = t; i < M * N; i += 256) {
+        float v = 0.f;
+#pragma unroll 4
+        for (int z = 0; z < KG; ++z) v += red[z * M * N + i];
+        outp[i] = v;
+    }
+}
+
+template <int M, int N>
+static int launch_dw_narrow(const float* dH, const float* X, const int32_t* row_map, const float* scale,
+                            const float* shift, float slope, float* partials, int64_t n, int splits, cudaStream_t st) {
+    constexpr int G = (M / 4) * (N / 4);
+    constexpr int KG = 256 / G;
+    constexpr int RS = dw_narrow_stage_rows(M, N, KG);
+    int64_t rows = ceil_div(n, splits);
+    rows = ceil_div(rows, RS) * RS;
+    dw_narrow_kernel<M, N><<<(unsigned)splits, 256, 0, st>>>(dH, X, row_map, scale, shift, slope, partials, n, rows);
+    return check_launch("dw_narrow");
+}
+
+// shapes of the Dual-DMP networks with both widths below 64 (Cout x Cin); 0 = not covered
+static int dw_narrow_shape(int32_t Cin, int32_t Cout) {
+    if (Cout == 32 && Cin == 16) return 1;
+    if (Cout == 64 && Cin == 32) return 2;
+    if (Cout == 32 && Cin == 64) return 3;
+    if (Cout == 16 && Cin == 32) return 4;
+    if (Cout == 4 && Cin == 16) return 5;
+    return 0;
+}
+
 static void dw_plan(int64_t n, int32_t Cin, int32_t Cout, int* splits, int64_t* kchunk) {
     int bm, bn;
     if (Cin > 64 && Cout > 64) { bm = 128; bn = 128; }
@@ -330,6 +518,20 @@ int ffma_gemm_dw(const float* dH, const float* X, const int32_t* row_map, const 
     dw_plan(n, Cin, Cout, &splits, &kc);
     DDMP_REQUIRE(workspace && workspace_bytes >= (int64_t)splits * Cin * Cout * (int64_t)sizeof(float),
                  "gemm_dw: workspace too small (%lld bytes)", (long long)workspace_bytes);
+    const int narrow = dw_narrow_shape(Cin, Cout);
+    if (narrow && splits > 1 && aligned16(dH) && aligned16(X) && aligned16(workspace)) {
+        float* P = reinterpret_cast<float*>(workspace);
+        int rc = DDMP_OK;
+        switch (narrow) {
+            case 1: rc = launch_dw_narrow<32, 16>(dH, X, row_map, scale, shift, slope, P, n, splits, st); break;
+            case 2: rc = launch_dw_narrow<64, 32>(dH, X, row_map, scale, shift, slope, P, n, splits, st); break;
+            case 3: rc = launch_dw_narrow<32, 64>(dH, X, row_map, scale, shift, slope, P, n, splits, st); break;
+            case 4: rc = launch_dw_narrow<16, 32>(dH, X, row_map, scale, shift, slope, P, n, splits, st); break;
+            default: rc = launch_dw_narrow<4, 16>(dH, X, row_map, scale, shift, slope, P, n, splits, st); break;
+        }
+        if (rc != DDMP_OK) return rc;
+        return launch_splitk_reduce(P, dW, (int64_t)Cin * Cout, splits, st);
+    }
     GemmArgs g{};
     g.A = dH; g.B = X; g.C = (splits == 1) ? dW : reinterpret_cast<float*>(workspace);
     g.a_map = nullptr; g.b_map = row_map;
@@ -339,10 +541,7 @@ int ffma_gemm_dw(const float* dH, const float* X, const int32_t* row_map, const 
     int rc = launch_by_shape<false, false, false, true>(g, splits, vec, st);
     if (rc != DDMP_OK) return rc;
     if (splits > 1) {
-        const int64_t count = (int64_t)Cin * Cout;
-        splitk_reduce_kernel<<<(unsigned)ceil_div(count, 256), 256, 0, st>>>(
-            reinterpret_cast<const float*>(workspace), dW, count, splits);
-        return check_launch("splitk_reduce");
+        return launch_splitk_reduce(reinterpret_cast<const float*>(workspace), dW, (int64_t)Cin * Cout, splits, st);
     }
     return DDMP_OK;
 }

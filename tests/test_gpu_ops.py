@@ -105,7 +105,7 @@ def test_spmm_reordered_graph_equals_permuted_reference(graphs):
     assert rel_err(Y.cpu(), ref[p]) < 2e-6
 
 
-SHAPES = [(7, 32), (16, 32), (32, 64), (64, 128), (128, 256), (256, 512), (512, 256), (64, 32), (32, 16), (20, 12)]
+SHAPES = [(7, 32), (16, 32), (32, 64), (64, 128), (128, 256), (256, 512), (512, 256), (64, 32), (32, 16), (20, 12), (16, 4)]
 
 
 @pytest.mark.parametrize("cin,cout", SHAPES)
@@ -137,6 +137,25 @@ def test_gemm_ffma(cin, cout, n):
     a = F_.gemm_dw(dHd, Xd[:n].contiguous(), cin, backend=1)
     b = F_.gemm_dw(dHd, Xd[:n].contiguous(), cin, backend=1)
     assert torch.equal(a, b)                                                    # split-K is deterministic
+
+
+@pytest.mark.parametrize("cin,cout", [(16, 32), (32, 64), (64, 32), (32, 16), (16, 4)])
+def test_gemm_dw_narrow_kernel_many_splits(cin, cout):
+    """dw_narrow_kernel (both widths < 64: 256-thread CTAs, split-K inside the CTA) with one partial per CTA for ~600
+    CTAs and a ragged last chunk, against float64; deterministic"""
+    from dual_dmp_b200 import functional as F_
+    n = 200003
+    torch.manual_seed(cin + cout)
+    X = torch.randn(n, cin); dH = torch.randn(n, cout)
+    scale, shift = torch.rand(cin) + 0.5, torch.randn(cin)
+    act = torch.nn.functional.leaky_relu(X.double() * scale.double() + shift.double(), 0.01)
+    Xd, dHd, sc, sh = X.to(DEV), dH.to(DEV), scale.to(DEV), shift.to(DEV)
+    a = F_.gemm_dw(dHd, Xd, cin, scale=sc, shift=sh)
+    e1 = rel_err(a, dH.double().t() @ act)
+    e2 = rel_err(F_.gemm_dw(dHd, Xd, cin), dH.double().t() @ X.double())
+    report(f"gemm_dw narrow cin={cin} cout={cout} n={n}", (e1, e2))
+    assert a.shape == (cout, cin) and max(e1, e2) < 2e-5, (e1, e2)
+    assert torch.equal(a, F_.gemm_dw(dHd, Xd, cin, scale=sc, shift=sh))
 
 
 @pytest.mark.parametrize("C", [32, 64, 256, 512])
