@@ -28,15 +28,16 @@ __device__ __forceinline__ void reduce_partials(const float* __restrict__ partia
     for (int s = 0; s < SETS; ++s) acc[s] = 0.0;
     if (c < C) {
         int64_t b = ty;
-        for (; b + 3 * kFinLanes < nblk; b += 4 * kFinLanes) {
-            float v[4][SETS];
+        constexpr int UN = 8;           // block rows in flight per lane: the loop is a chain of L2 round trips
+        for (; b + (UN - 1) * kFinLanes < nblk; b += UN * kFinLanes) {
+            float v[UN][SETS];
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
+            for (int u = 0; u < UN; ++u)
 #pragma unroll
                 for (int s = 0; s < SETS; ++s) v[u][s] = __ldg(partials + ((b + u * kFinLanes) * SETS + s) * C + c);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (MOMENTS) {          // b + 3*kFinLanes < nblk: none of these four is the last block
+            for (int u = 0; u < UN; ++u) {
+                if (MOMENTS) {          // b + (UN-1)*kFinLanes < nblk: none of these is the last block
                     acc[0] += (double)v[u][0];
                     acc[SETS - 1] += (double)v[u][SETS - 1] + (double)v[u][0] * (double)v[u][0] / (double)rows_per_block;
                 } else {
@@ -61,11 +62,31 @@ __device__ __forceinline__ void reduce_partials(const float* __restrict__ partia
 #pragma unroll
     for (int s = 0; s < SETS; ++s) red[ty][s][tx] = acc[s];
     __syncthreads();
+    // fold the lanes in lane order, in two levels (16 groups of 8 lanes, then the 16 group sums): 8 + 16 dependent adds
+    // instead of 128.  The result is valid in the threads with ty == 0 (threadIdx.x < kFinCh), the only ones that use it.
+    constexpr int GRP = 8;
+    if (ty < kFinLanes / GRP) {
+#pragma unroll
+        for (int s = 0; s < SETS; ++s) {
+            double t = 0.0;
+#pragma unroll
+            for (int y = 0; y < GRP; ++y) t += red[ty * GRP + y][s][tx];
+            acc[s] = t;
+        }
+    }
+    __syncthreads();
+    if (ty < kFinLanes / GRP) {
+#pragma unroll
+        for (int s = 0; s < SETS; ++s) red[ty][s][tx] = acc[s];
+    }
+    __syncthreads();
 #pragma unroll
     for (int s = 0; s < SETS; ++s) {
         double t = 0.0;
-#pragma unroll 8
-        for (int y = 0; y < kFinLanes; ++y) t += red[y][s][tx];
+        if (ty == 0) {
+#pragma unroll
+            for (int y = 0; y < kFinLanes / GRP; ++y) t += red[y][s][tx];
+        }
         out[s] = t;
     }
 }

@@ -1841,14 +1841,28 @@ __global__ void __launch_bounds__(PW * 32 + 32, 1) tc_gemm_tn_kernel(const TnArg
     }
 }
 
-// out[i] = sum_seg partials[seg][i] in segment order, float64 accumulate
-__global__ void seg_reduce_kernel(const float* __restrict__ partials, float* __restrict__ out, int64_t count,
-                                  int64_t segs) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count) return;
+// out[i] = sum_seg partials[seg][i], float64 accumulate, fixed order: a CTA owns 32 outputs, 8 z-lanes per output add
+// every 8th segment in ascending order (independent, coalesced loads) and the lane sums are folded in lane order.
+// (One thread per output walking all ~490 segments in a dependent chain took 74 us whatever the output size -- 18
+// launches, 1.1 ms per step at 1M faces.)
+__global__ void __launch_bounds__(256)
+seg_reduce_kernel(const float* __restrict__ partials, float* __restrict__ out, int64_t count, int64_t segs) {
+    __shared__ double red[8][33];
+    const int o = threadIdx.x & 31, zl = threadIdx.x >> 5;
+    const int64_t i = (int64_t)blockIdx.x * 32 + o;
     double s = 0.0;
-    for (int64_t z = 0; z < segs; ++z) s += (double)__ldg(partials + z * count + i);
-    out[i] = (float)s;
+    if (i < count) {
+#pragma unroll 4
+        for (int64_t z = zl; z < segs; z += 8) s += (double)__ldg(partials + z * count + i);
+    }
+    red[zl][o] = s;
+    __syncthreads();
+    if (zl == 0 && i < count) {
+        double v = red[0][o];
+#pragma unroll
+        for (int z = 1; z < 8; ++z) v += red[z][o];
+        out[i] = (float)v;
+    }
 }
 
 template <int BN, int STAGES, int PW>
@@ -2427,7 +2441,7 @@ int tc_gemm_dw(const float* dH, const float* X, const int32_t* row_map, const fl
         else if (Cin % 128 == 0) { h.tiles_n = Cin / 128; h.num_items = segs16 * h.tiles_m * h.tiles_n; rc16 = tc::launch_tn16<128, 3>(h, st); }
         else { h.tiles_n = Cin / 64; h.num_items = segs16 * h.tiles_m * h.tiles_n; rc16 = tc::launch_tn16<64, 4>(h, st); }
         if (rc16) return rc16;
-        tc::seg_reduce_kernel<<<(unsigned)ceil_div(count, 256), 256, 0, st>>>(h.P, dW, count, segs16);
+        tc::seg_reduce_kernel<<<(unsigned)ceil_div(count, 32), 256, 0, st>>>(h.P, dW, count, segs16);
         return check_launch("tc seg_reduce");
     }
     tc::TnArgs g{};
@@ -2440,7 +2454,7 @@ int tc_gemm_dw(const float* dH, const float* X, const int32_t* row_map, const fl
     else if (Cin % 128 == 0) { g.tiles_n = Cin / 128; g.num_items = segs * g.tiles_m * g.tiles_n; rc = tc::launch_tn<128, 3>(g, st); }
     else { g.tiles_n = Cin / 64; g.num_items = segs * g.tiles_m * g.tiles_n; rc = tc::launch_tn<64, 4>(g, st); }
     if (rc) return rc;
-    tc::seg_reduce_kernel<<<(unsigned)ceil_div(count, 256), 256, 0, st>>>(g.P, dW, count, segs);
+    tc::seg_reduce_kernel<<<(unsigned)ceil_div(count, 32), 256, 0, st>>>(g.P, dW, count, segs);
     return check_launch("tc seg_reduce");
 }
 
