@@ -494,7 +494,7 @@ static int launch_nt3(const Nt2Args& g0, cudaStream_t st);
 static int run_nt2(const float* A, const int* a_map, const float* scale, const float* shift, float slope,
                    const float* W, int transposed, void* workspace, float* C, int64_t M, int N, int K,
                    cudaStream_t st) {
-    const int BN = (N % 256 == 0) ? 256 : ((N % 128 == 0) ? 128 : 64);
+    const int BN = (N % 256 == 0) ? 256 : ((N % 128 == 0) ? 128 : ((N % 64 == 0) ? 64 : 32));
     uint8_t* img = reinterpret_cast<uint8_t*>(workspace);
     const int64_t chunks = (int64_t)N * (K / 4);
     if (nt2_kb() == 32) tc_prep_b_kernel<32><<<(unsigned)ceil_div(chunks, 256), 256, 0, st>>>(W, transposed, img, N, K, BN);
@@ -513,7 +513,8 @@ static int run_nt2(const float* A, const int* a_map, const float* scale, const f
     if (BN == 256 && two_cta && nt2_kb() == 32) return launch_nt3(g, st);
     if (BN == 256) return launch_nt2<256, 2>(g, st);
     if (BN == 128) return launch_nt2<128, 3>(g, st);
-    return launch_nt2<64, 4>(g, st);
+    if (BN == 64) return launch_nt2<64, 4>(g, st);
+    return launch_nt2<32, 4>(g, st);              // 32-wide outputs of the narrow layers (xw 64 -> 32, dx of 32 -> 64)
 }
 
 // ---- NT kernel, version 3: CTA pairs (cta_group::2) -----------------------------------------------------------------
@@ -2369,15 +2370,16 @@ static int launch_tn16x2(const Tn16Args& g, cudaStream_t st) {
 
 static inline bool tc_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-// The REDUCTION width of the NT kernels may be as small as 32 (one k-block of the 3xTF32 kernel): the 32 -> 64 forward
-// transform and the dH.W product of the 64 -> 32 layer then run on the tensor cores (1M rows: 0.118 vs 0.195 ms, 0.105
-// vs 0.153 ms on the FFMA kernel).  The OUTPUT width of an NT kernel stays >= 64; the TN kernel with a 32-row M tile
-// (dH^T.X of the 64 -> 32 layer) measured SLOWER than FFMA (0.342 vs 0.297 ms: it pays for a whole 128-row tile).
+// Both the reduction width and the output width of the NT kernels may be as small as 32 (one k-block / a 32-column UMMA
+// tile of the 3xTF32 kernel): at 1M rows X.W^T 32 -> 64 takes 0.118 ms instead of 0.195 on the FFMA kernel, dH.W of the
+// 64 -> 32 layer 0.105 instead of 0.153 (profiles/gemm_narrow_ab_r2.txt).  The TN kernel with a 32-row M tile (dH^T.X of
+// the 64 -> 32 layer) measured SLOWER than FFMA (0.342 vs 0.297 ms: it pays for a whole 128-row tile); the narrow dW
+// products have their own FFMA kernel (gemm_ffma.cu: dw_narrow_kernel).
 bool tc_supported_xw(int64_t n, int32_t Cin, int32_t Cout) {
-    return n > 0 && Cin >= 32 && Cout >= 64 && Cin % 32 == 0 && Cout % 64 == 0 && Cout <= 4096;
+    return n > 0 && Cin >= 32 && Cout >= 32 && Cin % 32 == 0 && Cout % 32 == 0 && Cout <= 4096;
 }
 bool tc_supported_dx(int64_t n, int32_t Cin, int32_t Cout) {
-    return n > 0 && Cin >= 64 && Cout >= 32 && Cout % 32 == 0 && Cin % 64 == 0 && Cin <= 4096;
+    return n > 0 && Cin >= 32 && Cout >= 32 && Cout % 32 == 0 && Cin % 32 == 0 && Cin <= 4096;
 }
 bool tc_supported_dw(int64_t n, int32_t Cin, int32_t Cout) {
     return n > 0 && Cin >= 64 && Cout >= 64 && Cin % 64 == 0 && Cout % 4 == 0 && Cin <= 4096 && Cout <= 4096;
@@ -2391,7 +2393,7 @@ int tc_gemm_xw(const float* X, const int32_t* row_map, const float* scale, const
     DDMP_REQUIRE(tc_aligned16(X) && tc_aligned16(W) && tc_aligned16(H), "tc_gemm_xw: pointers must be 16-byte aligned");
     DDMP_REQUIRE(workspace && tc_aligned16(workspace) && workspace_bytes >= tc_gemm_nt_workspace_bytes(Cin, Cout),
                  "tc_gemm_xw: workspace too small");
-    if (amax && amax_len > 0 && Cin % tc::BK16 == 0 && tc::f16_split_enabled())
+    if (amax && amax_len > 0 && Cin % tc::BK16 == 0 && Cout % 64 == 0 && tc::f16_split_enabled())
         return tc::run_nt16(X, row_map, scale, shift, slope, W, 0, workspace, H, n, Cout, Cin, amax, amax_len, st);
     return tc::run_nt2(X, row_map, scale, shift, slope, W, 0, workspace, H, n, Cout, Cin, st);
 }
@@ -2402,7 +2404,7 @@ int tc_gemm_dx(const float* dH, const float* W, float* gX, void* workspace, int6
     DDMP_REQUIRE(tc_aligned16(dH) && tc_aligned16(W) && tc_aligned16(gX), "tc_gemm_dx: pointers must be 16-byte aligned");
     DDMP_REQUIRE(workspace && tc_aligned16(workspace) && workspace_bytes >= tc_gemm_nt_workspace_bytes(Cin, Cout),
                  "tc_gemm_dx: workspace too small");
-    if (amax && amax_len > 0 && Cout % tc::BK16 == 0 && tc::f16_split_enabled())
+    if (amax && amax_len > 0 && Cout % tc::BK16 == 0 && Cin % 64 == 0 && tc::f16_split_enabled())
         return tc::run_nt16(dH, nullptr, nullptr, nullptr, 0.f, W, 1, workspace, gX, n, Cin, Cout, amax, amax_len, st);
     return tc::run_nt2(dH, nullptr, nullptr, nullptr, 0.f, W, 1, workspace, gX, n, Cin, Cout, st);
 }

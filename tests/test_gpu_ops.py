@@ -428,8 +428,18 @@ def test_gemm_tcgen05_narrow_reduction_width(n):
     assert torch.equal(g, F_.gemm_dx(dHd, W2d))
     d = F_.gemm_dw(dHd, X2d, 64, scale=sc2d, shift=sh2d)          # stays on the FFMA kernel (measured faster)
     e4 = rel_err(d, dH.double().t() @ act2)
-    report(f"gemm_tc narrow n={n}", (e1, e2, e3, e4))
-    assert max(e1, e2, e3) < 1e-5 and e4 < 2e-5, (e1, e2, e3, e4)
+    # 32-wide OUTPUTS (a 32-column UMMA tile): X.W^T of the 64 -> 32 layer (with an operand bound, as the network calls
+    # it: must not take the fp16-split kernel, whose tiles are >= 64 wide) and dH.W of the 32 -> 64 layer
+    bound = (act2.abs().amax(0) * 1.5).float().to(DEV)
+    h = F_.gemm_xw(X2d, W2d, scale=sc2d, shift=sh2d, backend=2, amax=bound)
+    e5 = rel_err(h, act2 @ W2.double().t())
+    assert h.shape == (n, 32) and torch.equal(h, F_.gemm_xw(X2d, W2d, scale=sc2d, shift=sh2d, amax=bound))
+    dH3 = torch.randn(n, 64); dH3d = dH3.to(DEV)
+    g3 = F_.gemm_dx(dH3d, Wd, backend=2, amax=dH3d.abs().amax().reshape(1))
+    e6 = rel_err(g3, dH3.double() @ W.double())
+    assert g3.shape == (n, 32) and torch.equal(g3, F_.gemm_dx(dH3d, Wd))
+    report(f"gemm_tc narrow n={n}", (e1, e2, e3, e4, e5, e6))
+    assert max(e1, e2, e3, e5, e6) < 1e-5 and e4 < 2e-5, (e1, e2, e3, e4, e5, e6)
 
 
 @pytest.mark.parametrize("cin,cout", TC_SHAPES)
