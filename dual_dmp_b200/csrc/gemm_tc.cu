@@ -1576,7 +1576,7 @@ static int launch_nt16x2(const Nt16Args& g0, cudaStream_t st) {
 }
 
 // switches of the fp16-split NT kernels (environment DDMP_TC_F16_FLAGS, ddmp_gemm_tc_flags): bit 0 = prefetch the next
-// tile's A rows into L2, bit 3 = unstaged epilogue, bit 4 = staged ld.shared + st.global epilogue instead of TMA stores
+// tile's A rows into L2, bit 1 = the same for K <= 256 only, bit 3 = unstaged epilogue, bit 4 = staged ld.shared + st.global epilogue instead of TMA stores
 int f16_flags(int set) {
     static std::atomic<int> v{-1};
     int cur = v.load(std::memory_order_relaxed);
@@ -1607,6 +1607,7 @@ static int run_nt16(const float* A, const int* a_map, const float* scale, const 
     g.A = A; g.Bimg = img; g.inv_sw = inv_sw; g.C = C; g.a_map = a_map; g.scale = scale; g.shift = shift;
     g.slope = slope; g.amax = amax; g.amax_len = amax_len;
     g.flags = f16_flags(-1);
+    if ((g.flags & 2) && K <= 256) g.flags |= 1;     // bit 1: the L2 prefetch only where it measured faster (K <= 256)
     static const bool trace = [] { const char* e = getenv("DDMP_TC_TRACE"); return e && e[0] == '1'; }();
     static unsigned long long* trace_buf = nullptr;
     if (trace) {

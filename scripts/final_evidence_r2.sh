@@ -1,21 +1,18 @@
 #!/bin/bash
-# Round-2 evidence on one B200: whole GPU test suite, smoke, the bench line (+ eager A/B), the reference arm, the ncu launch
-# list of two eager steps, DRAM traffic of the aggregation launches, ncu --set full of the dominant kernels.
+# Round-2 evidence on one B200: whole GPU test suite, smoke, the bench line, the reference arm (short budget), the ncu launch
+# list of two eager steps, DRAM traffic of the aggregation launches, ncu --set full of the dominant kernels, loss phase trace.
 set -u
 mkdir -p gpurun_out
-rm -f gpurun_out/parity.log gpurun_out/summary.txt
+rm -f gpurun_out/summary.txt
 nvidia-smi --query-gpu=name,driver_version,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
-for f in test_gpu_ops test_gpu_losses test_gpu_nets test_gpu_large test_gpu_parity_80k test_gpu_e2e_mad test_gpu_preprocess test_gpu_partition_loopback test_reference_driver test_gpu_partition; do
-  timeout 1500 python -m pytest tests/$f.py -m gpu -q --tb=short -p no:cacheprovider > gpurun_out/$f.log 2>&1
-  echo "$f exit=$? $(tail -n 1 gpurun_out/$f.log)" >> gpurun_out/summary.txt
-done
+timeout 1500 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider --durations=10 > gpurun_out/gpu_tests.log 2>&1
+echo "gpu tests exit=$? $(tail -n 1 gpurun_out/gpu_tests.log)" >> gpurun_out/summary.txt
 timeout 300 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1; echo "smoke exit=$? $(tail -n 1 gpurun_out/smoke.log)" >> gpurun_out/summary.txt
 timeout 1500 python bench.py --steps 20 --warmup 5 --detail gpurun_out/spmm_detail.json > gpurun_out/bench.json 2> gpurun_out/bench.err
 echo "bench exit=$?" >> gpurun_out/summary.txt
-timeout 600 python bench.py --steps 20 --warmup 5 --no-graph --no-cpu-baseline --no-small --no-e2e > gpurun_out/bench_eager.json 2> gpurun_out/bench_eager.err
-echo "bench eager exit=$?" >> gpurun_out/summary.txt
-timeout 900 python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err
+timeout 600 python bench.py --impl reference --steps 20 --warmup 5 --cpu-budget-s 60 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err
 echo "bench reference exit=$?" >> gpurun_out/summary.txt
+timeout 300 python scripts/bench_loss.py 224 1 > gpurun_out/loss_trace.txt 2>&1
 B="python bench.py --steps 2 --warmup 3 --no-graph --no-e2e --no-cpu-baseline --no-small --no-overlap"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 2400 -c 800 --csv \
   --log-file gpurun_out/launches_r2.csv $B > gpurun_out/launches_bench.log 2>&1
@@ -23,7 +20,7 @@ echo "ncu launch list exit=$? lines=$(wc -l < gpurun_out/launches_r2.csv)" >> gp
 timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:spmm \
   --launch-skip 288 -c 48 --csv --log-file gpurun_out/spmm_dram_r2.csv $B > gpurun_out/spmm_dram_bench.log 2>&1
 echo "ncu spmm dram exit=$? lines=$(wc -l < gpurun_out/spmm_dram_r2.csv)" >> gpurun_out/summary.txt
-timeout 1200 ncu --set full --clock-control none -k regex:"spmm|rowblock|tc_gemm|dual_loss" --csv --page raw \
+timeout 1200 ncu --set full --clock-control none -k regex:"spmm|rowblock|tc_gemm|dual_loss|dw_narrow" --csv --page raw \
   --log-file gpurun_out/ncu_full_r2_raw.csv python scripts/profile_ops_r2.py > gpurun_out/ncu_full.log 2>&1
 echo "ncu full exit=$? lines=$(wc -l < gpurun_out/ncu_full_r2_raw.csv)" >> gpurun_out/summary.txt
-cat gpurun_out/summary.txt; cat gpurun_out/bench.json
+cat gpurun_out/summary.txt; cat gpurun_out/bench.json; cat gpurun_out/bench_reference.json
