@@ -207,6 +207,220 @@ spmm_gcn_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, con
     }   // row blocks of this CTA
 }
 
+// ---- forward flavour of the wide layers (C = 256 / 512) with the Welford state in TENSOR MEMORY ------------------------
+// The kernel above keeps a private (mean, M2) pair per warp and channel in shared memory: 32 KB per CTA at C = 512,
+// 96 KB per SM -- taken from the L1 that serves the gathers, which is what makes the forward flavour 20-27 % slower than
+// the plain one (profiles/spmm_slice_ab_r2.txt: a shared-memory carve-out alone slows the PLAIN flavour past it).
+// Registers are no alternative (32 more per thread halve the occupancy).  But the SM has 256 KB of tensor memory that an
+// aggregation kernel never touches: a warp reads and writes its own 32 lanes x 8*NV columns with tcgen05.ld / tcgen05.st
+// (.32x32b: thread i <-> TMEM lane 32*(warp%4)+i), which is exactly "one private slot per thread".  State layout: warp w,
+// lane i, float4 index v: columns (w/4)*8*NV + 8*v + {0..3} = running mean, + {4..7} = M2.  64 columns per CTA at C = 512,
+// 32 at C = 256 (measured no faster there; off); 3 CTAs per SM allocate 192 of the 512 columns.  (The tcgen05 GEMM kernels of the other network's stream
+// fill the register file on their own, so an SM never hosts both kinds of CTA and tcgen05.alloc cannot wait on them.)
+// Same arithmetic and merge order as the kernel above: Y and the block moments are bitwise identical.
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float4& a, float4& b) {
+    uint32_t r0, r1, r2, r3, r4, r5, r6, r7;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7)
+                 : "r"(taddr)
+                 : "memory");
+    a = make_float4(__uint_as_float(r0), __uint_as_float(r1), __uint_as_float(r2), __uint_as_float(r3));
+    b = make_float4(__uint_as_float(r4), __uint_as_float(r5), __uint_as_float(r6), __uint_as_float(r7));
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float4& a, const float4& b) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+                 "r"(__float_as_uint(a.x)), "r"(__float_as_uint(a.y)), "r"(__float_as_uint(a.z)), "r"(__float_as_uint(a.w)),
+                 "r"(__float_as_uint(b.x)), "r"(__float_as_uint(b.y)), "r"(__float_as_uint(b.z)), "r"(__float_as_uint(b.w))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+template <int C, bool BIAS>
+__global__ void __launch_bounds__(256, 3)
+spmm_gcn_stats_tmem_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const float* __restrict__ w,
+                           const float* __restrict__ H, const float* __restrict__ bias, float* __restrict__ Y,
+                           float* __restrict__ partials, int64_t n, int rows_per_block) {
+    constexpr int NV = C / 128;             // float4 per lane
+    constexpr int GROUPS = 8;
+    constexpr int U = (NV >= 4) ? 2 : 4;
+    constexpr uint32_t WCOLS = 8 * NV;      // TMEM columns of one warp's state
+    constexpr uint32_t TCOLS = 2 * WCOLS < 32 ? 32 : 2 * WCOLS;
+    const int lane = threadIdx.x & 31;
+    const int gid = threadIdx.x >> 5;
+    __shared__ __align__(16) float red[GROUPS * 2 * 128];       // 8 KB merge buffer (128 channels per round)
+    __shared__ uint32_t tmem_slot;
+
+    if (gid == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         (uint32_t)__cvta_generic_to_shared(&tmem_slot)),
+                     "r"(TCOLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tbase = tmem_slot;
+    const uint32_t taddr = tbase + ((uint32_t)((gid & 3) * 32) << 16) + (uint32_t)(gid >> 2) * WCOLS;
+
+    const int64_t row0 = (int64_t)blockIdx.x * rows_per_block;
+    const int64_t row_end = (row0 + rows_per_block < n) ? (row0 + rows_per_block) : n;
+    {
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int v = 0; v < NV; ++v) tmem_st8(taddr + 8 * v, z, z);
+        tmem_wait_st();
+    }
+    float wcnt = 0.f;
+
+    int64_t r = row0 + gid;
+    int start = 0, end = 0, myc = 0;
+    float myw = 0.f;
+    if (r < row_end) {
+        start = __ldg(rowptr + r);
+        end = __ldg(rowptr + r + 1);
+        const int kk = start + lane;
+        if (kk < end) { myc = __ldg(col + kk); myw = __ldg(w + kk); }
+    }
+    for (; r < row_end; r += GROUPS) {
+        const int64_t rn = r + GROUPS;
+        int nstart = 0, nend = 0, nmyc = 0;
+        float nmyw = 0.f;
+        if (rn < row_end) {
+            nstart = __ldg(rowptr + rn);
+            nend = __ldg(rowptr + rn + 1);
+        }
+        float4 acc[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k0 = start; k0 < end; k0 += 32) {
+            if (k0 != start) {
+                const int kk = k0 + lane;
+                myc = (kk < end) ? __ldg(col + kk) : 0;
+                myw = (kk < end) ? __ldg(w + kk) : 0.f;
+            }
+            const int cnt = (end - k0 < 32) ? (end - k0) : 32;
+            int j = 0;
+            for (; j + U <= cnt; j += U) {
+                int cj[U];
+                float wj[U];
+                float4 x[U][NV];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    cj[u] = __shfl_sync(0xffffffffu, myc, j + u);
+                    wj[u] = __shfl_sync(0xffffffffu, myw, j + u);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const float* hp = H + (int64_t)cj[u] * C;
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) x[u][v] = ldg4(hp + (v * 32 + lane) * 4);
+                }
+                if (k0 == start && j == 0 && rn < row_end) {   // next row's first chunk, behind the gathers in flight
+                    const int kk = nstart + lane;
+                    if (kk < nend) { nmyc = __ldg(col + kk); nmyw = __ldg(w + kk); }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) {
+                        acc[v].x = fmaf(wj[u], x[u][v].x, acc[v].x);
+                        acc[v].y = fmaf(wj[u], x[u][v].y, acc[v].y);
+                        acc[v].z = fmaf(wj[u], x[u][v].z, acc[v].z);
+                        acc[v].w = fmaf(wj[u], x[u][v].w, acc[v].w);
+                    }
+                }
+            }
+            for (; j < cnt; ++j) {
+                const int c1 = __shfl_sync(0xffffffffu, myc, j);
+                const float w1 = __shfl_sync(0xffffffffu, myw, j);
+                const float* hp = H + (int64_t)c1 * C;
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    const float4 x = ldg4(hp + (v * 32 + lane) * 4);
+                    acc[v].x = fmaf(w1, x.x, acc[v].x);
+                    acc[v].y = fmaf(w1, x.y, acc[v].y);
+                    acc[v].z = fmaf(w1, x.z, acc[v].z);
+                    acc[v].w = fmaf(w1, x.w, acc[v].w);
+                }
+            }
+        }
+        if (rn < row_end && (end - start) < U) {     // short row: the prefetch slot inside the unrolled loop was skipped
+            const int kk = nstart + lane;
+            if (kk < nend) { nmyc = __ldg(col + kk); nmyw = __ldg(w + kk); }
+        }
+        // ---- epilogue: bias, store, Welford update of this warp's state in tensor memory ----
+        float4 s4[NV], q4[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) tmem_ld8(taddr + 8 * v, s4[v], q4[v]);
+        float* yp = Y + r * C;
+        wcnt += 1.f;
+        const float winv = 1.f / wcnt;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            if (BIAS) {
+                const float4 b = ldg4(bias + (v * 32 + lane) * 4);           // L1-resident; not worth 4*NV registers
+                acc[v].x += b.x; acc[v].y += b.y; acc[v].z += b.z; acc[v].w += b.w;
+            }
+            __stcs(reinterpret_cast<float4*>(yp + (v * 32 + lane) * 4), acc[v]);
+        }
+        tmem_wait_ld();
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            const float4 o = acc[v];
+            float4 s = s4[v], q = q4[v];
+            float d;
+            d = o.x - s.x; s.x = fmaf(d, winv, s.x); q.x = fmaf(d, o.x - s.x, q.x);
+            d = o.y - s.y; s.y = fmaf(d, winv, s.y); q.y = fmaf(d, o.y - s.y, q.y);
+            d = o.z - s.z; s.z = fmaf(d, winv, s.z); q.z = fmaf(d, o.z - s.z, q.z);
+            d = o.w - s.w; s.w = fmaf(d, winv, s.w); q.w = fmaf(d, o.w - s.w, q.w);
+            tmem_st8(taddr + 8 * v, s, q);
+        }
+        tmem_wait_st();
+        start = nstart; end = nend; myc = nmyc; myw = nmyw;
+    }
+
+    // merge the 8 warps channel-wise in warp order (Chan et al.), 128 channels per round through the 8 KB buffer
+    float* outp = partials + (int64_t)blockIdx.x * 2 * C;
+    const int rows_blk = (int)(row_end - row0);
+    float* myred = red + gid * 2 * 128;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        float4 s, q;
+        tmem_ld8(taddr + 8 * v, s, q);
+        tmem_wait_ld();
+        st4(myred + lane * 4, s);
+        st4(myred + 128 + lane * 4, q);
+        __syncthreads();
+        if (threadIdx.x < 128) {
+            const int ch = threadIdx.x;
+            float n_a = 0.f, mu = 0.f, m2 = 0.f;
+#pragma unroll 4
+            for (int g = 0; g < GROUPS; ++g) {
+                if (g < rows_blk) {
+                    const float n_b = (float)((rows_blk - g + GROUPS - 1) / GROUPS);
+                    const float mb = red[g * 256 + ch], qb = red[g * 256 + 128 + ch];
+                    const float nn = n_a + n_b;
+                    const float d = mb - mu;
+                    mu = fmaf(d, n_b / nn, mu);
+                    m2 += qb + d * d * (n_a * n_b / nn);
+                    n_a = nn;
+                }
+            }
+            outp[v * 128 + ch] = mu * n_a;
+            outp[C + v * 128 + ch] = m2;
+        }
+        __syncthreads();
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (gid == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(TCOLS) : "memory");
+    }
+}
+
 // Backward aggregation fused with the BatchNorm/LeakyReLU backward "apply":
 //     dH[i,:] = sum_k w[k] * dY[col[k],:],   dY = scale*(gZ - c1 - xhat*c2),  gZ = gX * lrelu'(scale*Y+shift)
 // dY is never written: it is recomputed from the gathered rows of gX and Y as  dY = scale*gZ + A - B*Y  with the
@@ -386,6 +600,15 @@ static int launch_spmm(const int* rowptr, const int* col, const float* w, const 
     while (bpc > 1 && ceil_div(nblk, bpc) < 8 * kNumSMs) --bpc;
     const unsigned grid = (unsigned)ceil_div(nblk, bpc);
     const int fl = spmm_flags();
+    if (partials && !amax_blocks && (fl & 4) && (C == 512 || (C == 256 && (fl & 8))) && bpc == 1) {
+        // widest forward flavour: Welford state in tensor memory (spmm_gcn_stats_tmem_kernel).  1M-row graphs, vertex /
+        // face: C = 512 0.592 -> 0.525 / 0.938 -> 0.862 ms; C = 256 (flag 8, off: its shared-memory state is only 16 KB
+        // per CTA) 0.332 -> 0.327 / 0.483 -> 0.498 ms (profiles/spmm_tmem_ab_r2.txt)
+        constexpr int CT = (C == 256 || C == 512) ? C : 256;
+        if (bias) spmm_gcn_stats_tmem_kernel<CT, true><<<(unsigned)nblk, 256, 0, st>>>(rowptr, col, w, H, bias, Y, partials, n, rpb);
+        else spmm_gcn_stats_tmem_kernel<CT, false><<<(unsigned)nblk, 256, 0, st>>>(rowptr, col, w, H, bias, Y, partials, n, rpb);
+        return check_launch("spmm_gcn_stats_tmem");
+    }
     if (partials) {
         if (bias) spmm_gcn_kernel<C, true, true><<<grid, 256, 0, st>>>(rowptr, col, w, H, bias, Y, partials, amax_blocks, n, rpb, bpc, fl);
         else spmm_gcn_kernel<C, true, false><<<grid, 256, 0, st>>>(rowptr, col, w, H, bias, Y, partials, amax_blocks, n, rpb, bpc, fl);

@@ -588,6 +588,47 @@ def test_spmm_tile_kernel_equals_gather_kernel_bitwise(kind, n, C):
         lib.query("ddmp_spmm_use_tile_kernel", prev)
 
 
+@pytest.mark.parametrize("C", [256, 512])
+@pytest.mark.parametrize("kind,n", [("ico", 3), ("open", 9), ("ico", 40)])
+def test_spmm_tensor_memory_statistics_kernel_equals_shared_memory_kernel_bitwise(kind, n, C):
+    """spmm_gcn_stats_tmem_kernel (forward flavour of the wide layers: per-warp Welford state in TMEM through
+    tcgen05.ld / tcgen05.st instead of 32 KB of shared memory; flag 4 of ddmp_spmm_use_tile_kernel) keeps the warp -> row
+    assignment, the per-element accumulation order and the Chan merge of spmm_gcn_kernel: Y and the (sum, M2) block
+    partials must be IDENTICAL -- with and without bias, ragged last block, partitioned layout, repeated launches (TMEM
+    allocation / release)."""
+    from dual_dmp_b200 import functional as F_
+    from dual_dmp_b200._lib import lib
+    from dual_dmp_b200.graph import GcnGraph
+    from oracle.step_ref import make_dataset
+    n_mesh, s_mesh, _ = small_case(kind, n)
+    ds = make_dataset(n_mesh, s_mesh)
+    V, F = len(n_mesh.vs), len(n_mesh.faces)
+    graphs_ = [GcnGraph(ds.edge_index, V, DEV, coords=ds.x_pos, reorder=True),
+               GcnGraph(ds.face_index, F, DEV, coords=ds.z2.detach()[:, :3], reorder=True)]
+    torch.manual_seed(C + n)
+    prev = lib.query("ddmp_spmm_use_tile_kernel", 0)
+    try:
+        for graph in graphs_:
+            H = torch.randn(graph.n, C, device=DEV)
+            b = torch.randn(C, device=DEV) * 3
+            n_own = graph.n - max(1, graph.n // 7)
+            rp = graph.rowptr[: n_own + 1].contiguous()
+            sub = type("G", (), dict(rowptr=rp, col=graph.col, w=graph.w, rowptr_t=rp, col_t=graph.col, w_t=graph.w))
+            res = {}
+            for flags in (2, 2 | 4 | 8, 4 | 8):
+                lib.query("ddmp_spmm_use_tile_kernel", 1 | (flags << 4))
+                out = []
+                for _ in range(3):
+                    out += [*F_.spmm_gcn(graph, H, bias=b, stats=True), *F_.spmm_gcn(graph, H, stats=True),
+                            *F_.spmm_gcn(sub, H, bias=b, stats=True, n_rows=n_own)]
+                res[flags] = out
+            for flags in (2 | 4 | 8, 4 | 8):
+                for i, (x, x0) in enumerate(zip(res[flags], res[2])):
+                    assert torch.equal(x, x0), (flags, i, graph.n, C)
+    finally:
+        lib.query("ddmp_spmm_use_tile_kernel", prev)
+
+
 @pytest.mark.parametrize("C", [32, 64, 128, 256, 512])
 @pytest.mark.parametrize("kind,n,which", [("open", 9, "vg"), ("open", 9, "fg"), ("ico", 3, "fg"), ("ico", 24, "vg"),
                                           ("ico", 24, "fg_id")])
