@@ -215,7 +215,7 @@ spmm_gcn_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, con
 // aggregation kernel never touches: a warp reads and writes its own 32 lanes x 8*NV columns with tcgen05.ld / tcgen05.st
 // (.32x32b: thread i <-> TMEM lane 32*(warp%4)+i), which is exactly "one private slot per thread".  State layout: warp w,
 // lane i, float4 index v: columns (w/4)*8*NV + 8*v + {0..3} = running mean, + {4..7} = M2.  64 columns per CTA at C = 512,
-// 32 at C = 256 (measured no faster there; off); 3 CTAs per SM allocate 192 of the 512 columns.  (The tcgen05 GEMM kernels of the other network's stream
+// 32 at C = 256; 3 (4 at C = 256) CTAs per SM allocate 192 (128) of the 512 columns.  (The tcgen05 GEMM kernels of the other network's stream
 // fill the register file on their own, so an SM never hosts both kinds of CTA and tcgen05.alloc cannot wait on them.)
 // Same arithmetic and merge order as the kernel above: Y and the block moments are bitwise identical.
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float4& a, float4& b) {
@@ -237,7 +237,7 @@ __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 template <int C, bool BIAS>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, C >= 512 ? 3 : 4)
 spmm_gcn_stats_tmem_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const float* __restrict__ w,
                            const float* __restrict__ H, const float* __restrict__ bias, float* __restrict__ Y,
                            float* __restrict__ partials, int64_t n, int rows_per_block) {
@@ -601,9 +601,10 @@ static int launch_spmm(const int* rowptr, const int* col, const float* w, const 
     const unsigned grid = (unsigned)ceil_div(nblk, bpc);
     const int fl = spmm_flags();
     if (partials && !amax_blocks && (fl & 4) && (C == 512 || (C == 256 && (fl & 8))) && bpc == 1) {
-        // widest forward flavour: Welford state in tensor memory (spmm_gcn_stats_tmem_kernel).  1M-row graphs, vertex /
-        // face: C = 512 0.592 -> 0.525 / 0.938 -> 0.862 ms; C = 256 (flag 8, off: its shared-memory state is only 16 KB
-        // per CTA) 0.332 -> 0.327 / 0.483 -> 0.498 ms (profiles/spmm_tmem_ab_r2.txt)
+        // wide forward flavour: Welford state in tensor memory (spmm_gcn_stats_tmem_kernel; flag 4: C = 512, flag 8:
+        // C = 256).  1M-row graphs, vertex / face: C = 512 0.592 -> 0.525 / 0.938 -> 0.862 ms; C = 256 0.331 -> 0.296 /
+        // 0.483 -> 0.449 ms once the kernel runs 4 CTAs per SM (at 3 it measured the same as the 16 KB shared-memory
+        // state): profiles/spmm_tmem_ab_r2.txt
         constexpr int CT = (C == 256 || C == 512) ? C : 256;
         if (bias) spmm_gcn_stats_tmem_kernel<CT, true><<<(unsigned)nblk, 256, 0, st>>>(rowptr, col, w, H, bias, Y, partials, n, rpb);
         else spmm_gcn_stats_tmem_kernel<CT, false><<<(unsigned)nblk, 256, 0, st>>>(rowptr, col, w, H, bias, Y, partials, n, rpb);

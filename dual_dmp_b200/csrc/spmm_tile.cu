@@ -464,7 +464,7 @@ int spmm_bn_bwd_tile_launch(const int* rowptr, const int* col, const float* w, c
 //   flags bit 1 = streaming (evict-first) stores of Y in the gather kernel (default on: Y is never re-read from L2 by this
 //   kernel, and keeping it out leaves the cache to the gathered rows: +1 % on the wide layers).  -1: not decided yet.
 static std::atomic<int> g_tile_mode{-1};
-constexpr int kDefaultSetting = 1 | ((2 | 4) << 4);      // tile kernel for C <= 128, streaming stores, TMEM Welford state at C = 512
+constexpr int kDefaultSetting = 1 | ((2 | 4 | 8) << 4);  // tile kernel for C <= 128, streaming stores, TMEM Welford state at C = 256 / 512
 
 static int tile_setting() {
     int v = g_tile_mode.load(std::memory_order_relaxed);

@@ -74,7 +74,7 @@ int ddmp_spmm_gcn(const int32_t* rowptr, const int32_t* col, const float* w, con
                   float* Y, float* stats_partials, float* amax_blocks, int64_t n, int32_t C, void* stream);
 /* number of floats ddmp_spmm_gcn writes to amax_blocks for this shape */
 int64_t ddmp_spmm_amax_len(int64_t n, int32_t C);
-/* Kernel choice of ddmp_spmm_gcn (environment DDMP_SPMM_TILE, default 97).  setting = mode | flags << 4.
+/* Kernel choice of ddmp_spmm_gcn (environment DDMP_SPMM_TILE, default 225).  setting = mode | flags << 4.
  * mode: 0 = gather-only kernel for every width, 1 = tile-staged kernel for C <= 128 (where it measures faster on B200),
  * 2 = tile-staged kernel for every mesh width (A/B measurements, bit-exactness test between the two kernels).
  * flags: 2 = streaming stores of Y in the gather kernel; 4 = forward flavour (bias + BatchNorm moments) at C = 512 with the
