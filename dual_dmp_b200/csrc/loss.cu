@@ -463,6 +463,22 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     }
 }
 
+// see ddmp_gather_flat
+constexpr int kGatherMax = 80;
+struct GatherArgs {
+    const float* src[kGatherMax];
+    int64_t off[kGatherMax];
+    int64_t cnt[kGatherMax];
+    int n;
+};
+__global__ void __launch_bounds__(256) gather_flat_kernel(const GatherArgs a, float* __restrict__ dst) {
+    const int s = blockIdx.y;
+    const float* __restrict__ src = a.src[s];
+    float* __restrict__ out = dst + a.off[s];
+    const int64_t cnt = a.cnt[s];
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < cnt; i += (int64_t)gridDim.x * 256) out[i] = src[i];
+}
+
 }  // namespace ddmp
 
 #define LAUNCH_1D(kernel, count, st, ...) \
@@ -676,6 +692,35 @@ int ddmp_adam_step_dev(float* param, const float* grad, float* exp_avg, float* e
     LAUNCH_1D(adam_kernel, count, as_stream(stream), param, grad, exp_avg, exp_avg_sq, clip_norm, max_norm, lr,
               beta1, beta2, eps, 1.f, 1.f, (const int64_t*)step_counter, count);
     return check_launch("adam_step_dev");
+}
+
+// Flat gradient of a network: the gradient tensors autograd hands back (one per parameter) copied into one buffer in
+// parameter order by ONE launch.  The (pointer, offset, count) triples travel as a kernel argument, so a CUDA-graph
+// replay needs no pointer table in memory (graph-captured allocations keep their addresses).
+int ddmp_gather_flat(const void* const* srcs, const int64_t* offsets, const int64_t* counts, int32_t n_src, float* dst,
+                     void* stream) {
+    using namespace ddmp;
+    DDMP_REQUIRE(srcs && offsets && counts && dst && n_src >= 0, "gather_flat: bad arguments");
+    cudaStream_t st = as_stream(stream);
+    for (int base = 0; base < n_src; base += kGatherMax) {
+        GatherArgs a{};
+        a.n = (n_src - base < kGatherMax) ? (n_src - base) : kGatherMax;
+        int64_t longest = 0;
+        for (int i = 0; i < a.n; ++i) {
+            DDMP_REQUIRE(srcs[base + i] != nullptr && counts[base + i] >= 0 && offsets[base + i] >= 0, "gather_flat: bad segment");
+            a.src[i] = static_cast<const float*>(srcs[base + i]);
+            a.off[i] = offsets[base + i];
+            a.cnt[i] = counts[base + i];
+            if (a.cnt[i] > longest) longest = a.cnt[i];
+        }
+        if (longest == 0) continue;
+        int64_t bx = ceil_div(longest, 256 * 4);
+        if (bx > 64) bx = 64;
+        gather_flat_kernel<<<dim3((unsigned)bx, (unsigned)a.n), 256, 0, st>>>(a, dst);
+        int rc = check_launch("gather_flat");
+        if (rc != DDMP_OK) return rc;
+    }
+    return DDMP_OK;
 }
 
 }  // extern "C"

@@ -193,6 +193,12 @@ class FusedAdam:
             self.flat[off: off + k].copy_(p.detach().reshape(-1))
             p.data = self.flat[off: off + k].view_as(p)
             off += k
+        import ctypes
+        counts = [p.numel() for p in self.params]
+        offsets = [sum(counts[:i]) for i in range(len(counts))]
+        self._counts = (ctypes.c_int64 * len(counts))(*counts)
+        self._offsets = (ctypes.c_int64 * len(counts))(*offsets)
+        self.gflat = torch.empty_like(self.flat)           # flat gradient, filled by ddmp_gather_flat every step
         self.exp_avg = torch.zeros_like(self.flat)
         self.exp_avg_sq = torch.zeros_like(self.flat)
         self.step_count = torch.zeros((), dtype=torch.int64, device=dev)
@@ -209,7 +215,11 @@ class FusedAdam:
         from ._lib import lib, ptr, set_device, stream_ptr
         set_device(self.device)
         st = stream_ptr(self.device)
-        g = torch.cat([p.grad.reshape(-1) for p in self.params])        # flat gradient (one gather kernel)
+        import ctypes
+        grads = [p.grad if p.grad.is_contiguous() else p.grad.contiguous() for p in self.params]
+        srcs = (ctypes.c_void_p * len(grads))(*[t.data_ptr() for t in grads])
+        g = self.gflat                                                   # flat gradient: one library launch
+        lib.call("ddmp_gather_flat", srcs, self._offsets, self._counts, len(grads), ptr(g), st)
         clip = None
         if self.max_norm is not None:
             lib.call("ddmp_grad_norm", ptr(g), ptr(self.norm), ptr(self.scratch), g.numel(), st)

@@ -346,6 +346,13 @@ int ddmp_adam_step_dev(float* param, const float* grad, float* exp_avg, float* e
                        float max_norm, float lr, float beta1, float beta2, float eps, int64_t* step_counter,
                        int64_t count, void* stream);
 
+/* The gradients of one network (n_src device tensors of counts[i] floats each) copied to dst + offsets[i] by one launch
+ * per 80 tensors: the flat gradient ddmp_grad_norm / ddmp_adam_step_dev consume.  srcs / offsets / counts are HOST arrays;
+ * they travel as kernel arguments (frozen at CUDA-graph capture together with the -- stable -- addresses).
+ * [ref: main.py:107-110: loss.backward() leaves one .grad per parameter; the optimizer walks them] */
+int ddmp_gather_flat(const void* const* srcs, const int64_t* offsets, const int64_t* counts, int32_t n_src, float* dst,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif
