@@ -165,8 +165,6 @@ struct Nt2Args {
     int N, K;
     int tiles_n;
     int64_t num_tiles;
-    int knockout;         // profiling only (DDMP_TC_KNOCKOUT): 1 = no A loads, 2 = no A loads/stores, 4 = no C stores,
-                          // 8 = no B bulk copies (results are garbage; timing only)
 };
 
 // W [N,K] (or, transposed, W^T given as [K,N]) -> image; one thread per (n, 16-byte chunk of K)
@@ -266,15 +264,14 @@ __global__ void __launch_bounds__(kV2Threads, 1) tc_gemm_nt2_kernel(const Nt2Arg
                     float4 av[NJ];
 #pragma unroll
                     for (int j = 0; j < NJ; ++j)
-                        av[j] = (src_row[j] >= 0 && !(g.knockout & 3)) ? ldg4(g.A + src_row[j] * g.K + k0)
-                                                                       : make_float4(1.f, 2.f, 3.f, 4.f);
+                        av[j] = (src_row[j] >= 0) ? ldg4(g.A + src_row[j] * g.K + k0)
+                                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
                     float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (has_act) { sc = ldg4(g.scale + k0); sh = ldg4(g.shift + k0); }
                     mbar_wait(empty_bar + s, ph ^ 1u);
                     const uint32_t st = smem_base + s * STAGE_BYTES;
 #pragma unroll
                     for (int j = 0; j < NJ; ++j) {
-                        if (g.knockout & 2) break;
                         const uint32_t row = (t / CPR) + j * RPP;
                         float4 a = av[j];
                         if (has_act && src_row[j] >= 0) {
@@ -405,7 +402,6 @@ __global__ void __launch_bounds__(kV2Threads, 1) tc_gemm_nt2_kernel(const Nt2Arg
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
                     mbar_wait(empty_bar + s, ph ^ 1u);
-                    if (g.knockout & 8) { mbar_arrive(full_bar + s); continue; }
                     mbar_arrive_expect_tx(full_bar + s, 2 * B_BYTES);
                     bulk_g2s(smem_base + s * STAGE_BYTES + 2 * A_BYTES, src + (int64_t)kb * (2 * (int64_t)B_BYTES),
                              2 * B_BYTES, full_bar + s);
@@ -443,7 +439,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) tc_gemm_nt2_kernel(const Nt2Arg
                                  : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w)
                                  : "r"(stg + (uint32_t)r * 128u + (uint32_t)((cc ^ (r & 7)) << 4)));
                     const int64_t m = mrow0 + r;
-                    if (m < g.M && !(g.knockout & 4))
+                    if (m < g.M)
                         *reinterpret_cast<uint4*>(g.C + m * g.N + n0 + cb + cc * 4) = o;
                 }
                 __syncwarp();
@@ -473,22 +469,13 @@ static int launch_nt2_impl(const Nt2Args& g, cudaStream_t st) {
     tc_gemm_nt2_kernel<BN, STAGES, DEEP, KB><<<(unsigned)grid, kV2Threads, smem, st>>>(g);
     return check_launch("tc_gemm_nt2");
 }
-// K-block: 32 (SWIZZLE_128B, default) or 16 (SWIZZLE_64B, twice the stages; DDMP_TC_BK=16).  Measured on B200
-// (profiles/gemm_ab_r1.txt): 32 is 10-15 % faster, and the 2-deep register prefetch (DDMP_TC_DEEP=1) is 8 % slower
-// than issuing the loads at the top of the iteration -> the kernel is throughput-, not latency-bound.
-static int nt2_kb() {
-    static const int v = [] { const char* e = getenv("DDMP_TC_BK"); return (e && atoi(e) == 16) ? 16 : 32; }();
-    return v;
-}
+// K-block: 32 fp32 = one 128-byte swizzle row.  Measured on B200 (profiles/gemm_ab_r1.txt): a 16-wide k-block
+// (SWIZZLE_64B, twice the stages) is 10-15 % slower, and a 2-deep register prefetch 8 % slower than issuing the loads at the
+// top of the iteration -- the kernel is throughput-, not latency-bound; both variants were dropped.
 template <int BN, int STAGES32>
 static int launch_nt2(const Nt2Args& g, cudaStream_t st) {
-    static const bool deep = [] { const char* e = getenv("DDMP_TC_DEEP"); return e && e[0] == '1'; }();
-    if (nt2_kb() == 32)
-        return deep ? launch_nt2_impl<BN, STAGES32, true, 32>(g, st) : launch_nt2_impl<BN, STAGES32, false, 32>(g, st);
-    return deep ? launch_nt2_impl<BN, 2 * STAGES32, true, 16>(g, st) : launch_nt2_impl<BN, 2 * STAGES32, false, 16>(g, st);
+    return launch_nt2_impl<BN, STAGES32, false, 32>(g, st);
 }
-
-static int launch_nt3(const Nt2Args& g0, cudaStream_t st);
 
 // B = W [N,K] row-major (transposed == 0) or B = W^T where W is [K,N] row-major (transposed == 1)
 static int run_nt2(const float* A, const int* a_map, const float* scale, const float* shift, float slope,
@@ -497,8 +484,7 @@ static int run_nt2(const float* A, const int* a_map, const float* scale, const f
     const int BN = (N % 256 == 0) ? 256 : ((N % 128 == 0) ? 128 : ((N % 64 == 0) ? 64 : 32));
     uint8_t* img = reinterpret_cast<uint8_t*>(workspace);
     const int64_t chunks = (int64_t)N * (K / 4);
-    if (nt2_kb() == 32) tc_prep_b_kernel<32><<<(unsigned)ceil_div(chunks, 256), 256, 0, st>>>(W, transposed, img, N, K, BN);
-    else tc_prep_b_kernel<16><<<(unsigned)ceil_div(chunks, 256), 256, 0, st>>>(W, transposed, img, N, K, BN);
+    tc_prep_b_kernel<32><<<(unsigned)ceil_div(chunks, 256), 256, 0, st>>>(W, transposed, img, N, K, BN);
     int rc = check_launch("tc_prep_b");
     if (rc) return rc;
     Nt2Args g{};
@@ -506,27 +492,20 @@ static int run_nt2(const float* A, const int* a_map, const float* scale, const f
     g.M = M; g.N = N; g.K = K; g.tiles_n = N / BN;
     g.num_tiles = ceil_div(M, BM) * g.tiles_n;
     DDMP_REQUIRE(g.num_tiles < (1ll << 31), "tc gemm: too many tiles");
-    static const int knockout = [] { const char* e = getenv("DDMP_TC_KNOCKOUT"); return e ? atoi(e) : 0; }();
-    g.knockout = knockout;
-    if (knockout) { static bool said = false; if (!said) { fprintf(stderr, "[ddmp] tc knockout=%d\n", knockout); said = true; } }
-    static const bool two_cta = [] { const char* e = getenv("DDMP_TC_2CTA"); return e && e[0] == '1'; }();
-    if (BN == 256 && two_cta && nt2_kb() == 32) return launch_nt3(g, st);
     if (BN == 256) return launch_nt2<256, 2>(g, st);
     if (BN == 128) return launch_nt2<128, 3>(g, st);
     if (BN == 64) return launch_nt2<64, 4>(g, st);
     return launch_nt2<32, 4>(g, st);              // 32-wide outputs of the narrow layers (xw 64 -> 32, dx of 32 -> 64)
 }
 
-// ---- NT kernel, version 3: CTA pairs (cta_group::2) -----------------------------------------------------------------
-// Two CTAs of one cluster (same TPC) compute a 256 x 256 tile with M=256 MMAs issued by the leader CTA: each CTA
-// stages its own 128 rows of A and only HALF of the B tile (128 of the 256 weight rows), the tensor core reads both
-// halves, and each CTA's TMEM receives its 128 output rows.  Per CTA and k-block this cuts the shared-memory traffic
-// from 240 KB to 160 KB (B operand reads and bulk-copy writes halve), which is what bounds version 2 (ncu: shared
-// pipe 82 % busy at 75 % tensor-pipe activity), and frees room for a third pipeline stage.
-// Synchronisation across the pair: the peer's producers/B-loader arrive on the peer's own `full` barrier; a relay
-// thread there forwards it to the leader's `peer_ready` barrier (remote mbarrier arrive); tcgen05.commit with the
-// multicast mask 0b11 releases a stage / publishes the accumulator in both CTAs; the peer's epilogue warps arrive
-// remotely on the leader's `acc_empty`.
+// ---- CTA pairs (cta_group::2): helpers of the fp16-split pair kernels below ---------------------------------------------
+// Two CTAs of one cluster (same TPC) compute a 256-row tile with M=256 MMAs issued by the leader CTA: each CTA stages its
+// own 128 rows of A and only HALF of the B tile, the tensor core reads both halves, and each CTA's TMEM receives its 128
+// output rows.  Synchronisation across the pair: the peer's producers / B-loader arrive on the peer's own `full` barrier; a
+// relay thread there forwards it to the leader's `peer_ready` barrier (remote mbarrier arrive); tcgen05.commit with the
+// multicast mask 0b11 releases a stage / publishes the accumulator in both CTAs; the peer's epilogue warps arrive remotely
+// on the leader's `acc_empty`.  (The 3xTF32 pair kernel this scheme was first built for, round 1, gained 0-4 % over the
+// single-CTA kernel and was removed when the fp16 split became the default.)
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -573,238 +552,6 @@ __device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
         "h"((uint16_t)3)
         : "memory");
 }
-__device__ __forceinline__ void umma_tf32_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                               uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-
-constexpr int kNt3Stages = 3;
-constexpr int kNt3BN = 256;
-
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kV2Threads, 1) tc_gemm_nt3_kernel(const Nt2Args g) {
-    constexpr int STAGES = kNt3Stages;
-    constexpr int BN = kNt3BN;
-    constexpr uint32_t A_BYTES = BM * 128;               // this CTA's 128 rows, one of hi / lo
-    constexpr uint32_t B_HALF = (BN / 2) * 128;          // this CTA's half of the B tile, one of hi / lo
-    constexpr uint32_t B_FULL = BN * 128;
-    constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_HALF;
-    constexpr uint32_t TMEM_COLS = 2 * BN;
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-    uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* peer_ready = empty_bar + STAGES;           // leader only: the peer's stage is filled
-    uint64_t* acc_full = peer_ready + STAGES;            // [2]
-    uint64_t* acc_empty = acc_full + 2;                  // [2] leader only: both CTAs drained the buffer
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-    uint8_t* staging = smem + STAGES * STAGE_BYTES + 256;
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank = cluster_ctarank();
-    const int num_kb = g.K / BK;
-    const int64_t num_pairs = gridDim.x / 2, pair = blockIdx.x / 2;
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) {
-            mbar_init(full_bar + s, kProducerWarps + 1);
-            mbar_init(empty_bar + s, 1);
-            mbar_init(peer_ready + s, 1);
-        }
-        for (int b = 0; b < 2; ++b) {
-            mbar_init(acc_full + b, 1);
-            mbar_init(acc_empty + b, 8);                 // 4 local + 4 remote epilogue warps
-        }
-        fence_barrier_init();
-    }
-    cluster_sync_all();                                  // barriers of both CTAs exist before any remote arrive
-    if (warp == 8) tmem_alloc_2cta(tmem_slot, TMEM_COLS);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    const uint32_t smem_base = smem_u32(smem);
-
-    if (warp < kProducerWarps) {
-        // ===== A producers (this CTA's 128 rows of the 256-row pair tile) =====
-        const int t = threadIdx.x;
-        const uint32_t c = t & 7;
-        const bool has_act = g.scale != nullptr;
-        constexpr int NJ = BM * 8 / kProducerThreads;
-        uint32_t it = 0;
-        for (int64_t tile = pair; tile < g.num_tiles; tile += num_pairs) {
-            const int64_t m0 = (tile / g.tiles_n) * (2 * BM) + rank * BM;
-            int64_t src_row[NJ];
-#pragma unroll
-            for (int j = 0; j < NJ; ++j) {
-                const int64_t m = m0 + (t >> 3) + j * (kProducerThreads / 8);
-                src_row[j] = (m < g.M) ? (g.a_map ? (int64_t)__ldg(g.a_map + m) : m) : -1;
-            }
-            for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
-                const int k0 = kb * BK + c * 4;
-                float4 av[NJ];
-#pragma unroll
-                for (int j = 0; j < NJ; ++j)
-                    av[j] = (src_row[j] >= 0) ? ldg4(g.A + src_row[j] * g.K + k0) : make_float4(0.f, 0.f, 0.f, 0.f);
-                float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (has_act) { sc = ldg4(g.scale + k0); sh = ldg4(g.shift + k0); }
-                mbar_wait_cluster(empty_bar + s, ph ^ 1u);
-                const uint32_t st = smem_base + s * STAGE_BYTES;
-#pragma unroll
-                for (int j = 0; j < NJ; ++j) {
-                    const uint32_t row = (t >> 3) + j * (kProducerThreads / 8);
-                    float4 a = av[j];
-                    if (has_act && src_row[j] >= 0) {
-                        a.x = lrelu_max(fmaf(a.x, sc.x, sh.x), g.slope); a.y = lrelu_max(fmaf(a.y, sc.y, sh.y), g.slope);
-                        a.z = lrelu_max(fmaf(a.z, sc.z, sh.z), g.slope); a.w = lrelu_max(fmaf(a.w, sc.w, sh.w), g.slope);
-                    }
-                    uint4 hi, lo;
-                    split_tf32(a.x, hi.x, lo.x); split_tf32(a.y, hi.y, lo.y);
-                    split_tf32(a.z, hi.z, lo.z); split_tf32(a.w, hi.w, lo.w);
-                    const uint32_t off = sw128(row, c);
-                    sts128(st + off, hi);
-                    sts128(st + A_BYTES + off, lo);
-                }
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(full_bar + s);
-            }
-        }
-    } else if (warp == 8) {
-        if (lane == 0) {
-            uint32_t it = 0, tile_no = 0;
-            if (rank == 0) {
-                // ===== MMA issuer (leader CTA): M = 256 across the pair =====
-                constexpr uint32_t idesc = make_idesc(2 * BM, BN, false, false);
-                for (int64_t tile = pair; tile < g.num_tiles; tile += num_pairs, ++tile_no) {
-                    const uint32_t buf = tile_no & 1u;
-                    mbar_wait_cluster(acc_empty + buf, ((tile_no >> 1) & 1u) ^ 1u);
-                    tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + buf * BN;
-                    for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                        const int s = it % STAGES;
-                        const uint32_t ph = (it / STAGES) & 1;
-                        mbar_wait(full_bar + s, ph);
-                        mbar_wait_cluster(peer_ready + s, ph);
-                        tc_fence_after();
-                        const uint32_t sa = smem_base + s * STAGE_BYTES;
-#pragma unroll
-                        for (int ks = 0; ks < BK / UMMA_K; ++ks) {
-                            const uint32_t koff = ks * UMMA_K * 4;
-                            const uint64_t a_hi = make_desc(sa + koff, 16, 1024);
-                            const uint64_t a_lo = make_desc(sa + A_BYTES + koff, 16, 1024);
-                            const uint64_t b_hi = make_desc(sa + 2 * A_BYTES + koff, 16, 1024);
-                            const uint64_t b_lo = make_desc(sa + 2 * A_BYTES + B_HALF + koff, 16, 1024);
-                            umma_tf32_2cta(d_tmem, a_lo, b_hi, idesc, (kb | ks) != 0);
-                            umma_tf32_2cta(d_tmem, a_hi, b_lo, idesc, 1);
-                            umma_tf32_2cta(d_tmem, a_hi, b_hi, idesc, 1);
-                        }
-                        umma_commit_2cta(empty_bar + s);         // frees stage s in BOTH CTAs
-                    }
-                    umma_commit_2cta(acc_full + buf);            // accumulator ready in BOTH CTAs
-                }
-            } else {
-                // ===== relay (peer CTA): forward "my stage is filled" to the leader =====
-                for (int64_t tile = pair; tile < g.num_tiles; tile += num_pairs) {
-                    for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                        const int s = it % STAGES;
-                        const uint32_t ph = (it / STAGES) & 1;
-                        mbar_wait(full_bar + s, ph);
-                        mbar_arrive_remote(peer_ready + s, 0);
-                    }
-                }
-            }
-        }
-        __syncwarp();
-    } else if (warp == 9) {
-        // ===== B loader: this CTA's half of the weight tile (hi half + lo half) =====
-        if (lane == 0) {
-            uint32_t it = 0;
-            for (int64_t tile = pair; tile < g.num_tiles; tile += num_pairs) {
-                const int tn = (int)(tile % g.tiles_n);
-                const uint8_t* src = g.Bimg + (int64_t)tn * num_kb * (2 * (int64_t)B_FULL) + (int64_t)rank * B_HALF;
-                for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                    const int s = it % STAGES;
-                    const uint32_t ph = (it / STAGES) & 1;
-                    mbar_wait_cluster(empty_bar + s, ph ^ 1u);
-                    mbar_arrive_expect_tx(full_bar + s, 2 * B_HALF);
-                    const uint8_t* sk = src + (int64_t)kb * (2 * (int64_t)B_FULL);
-                    const uint32_t dst = smem_base + s * STAGE_BYTES + 2 * A_BYTES;
-                    bulk_g2s(dst, sk, B_HALF, full_bar + s);
-                    bulk_g2s(dst + B_HALF, sk + B_FULL, B_HALF, full_bar + s);
-                }
-            }
-        }
-        __syncwarp();
-    } else if (warp >= 12) {
-        // ===== epilogue (each CTA drains its own 128 rows) =====
-        const int q = warp & 3;
-        const uint32_t stg = smem_u32(staging) + (uint32_t)q * (32u * 128u);
-        uint32_t tile_no = 0;
-        for (int64_t tile = pair; tile < g.num_tiles; tile += num_pairs, ++tile_no) {
-            const uint32_t buf = tile_no & 1u;
-            const int64_t mrow0 = (tile / g.tiles_n) * (2 * BM) + rank * BM + q * 32;
-            const int n0 = (int)(tile % g.tiles_n) * BN;
-            mbar_wait_cluster(acc_full + buf, (tile_no >> 1) & 1u);
-            tc_fence_after();
-#pragma unroll 1
-            for (int cb = 0; cb < BN; cb += 32) {
-                uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)cb, v);
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    sts128(stg + (uint32_t)lane * 128u + (uint32_t)((i ^ (lane & 7)) << 4),
-                           make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
-                __syncwarp();
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int r = j * 4 + (lane >> 3), cc = lane & 7;
-                    uint4 o;
-                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                                 : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w)
-                                 : "r"(stg + (uint32_t)r * 128u + (uint32_t)((cc ^ (r & 7)) << 4)));
-                    const int64_t m = mrow0 + r;
-                    if (m < g.M) *reinterpret_cast<uint4*>(g.C + m * g.N + n0 + cb + cc * 4) = o;
-                }
-                __syncwarp();
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-                if (rank == 0) mbar_arrive(acc_empty + buf);
-                else mbar_arrive_remote(acc_empty + buf, 0);
-            }
-        }
-    }
-    tc_fence_before();
-    cluster_sync_all();                                  // neither CTA may exit while the other can still reach it
-    if (warp == 8) {
-        tc_fence_after();
-        tmem_dealloc_2cta(tmem_base, TMEM_COLS);
-    }
-}
-
-static int launch_nt3(const Nt2Args& g0, cudaStream_t st) {
-    constexpr size_t smem = (size_t)kNt3Stages * (2 * BM * 128 + 2 * (kNt3BN / 2) * 128) + 1024 + 256 + 4 * 32 * 128;
-    static PerDeviceOnce configured;
-    if (configured.need()) {
-        DDMP_CUDA(cudaFuncSetAttribute(tc_gemm_nt3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured.mark();
-    }
-    Nt2Args g = g0;
-    g.num_tiles = ceil_div(g.M, 2 * BM) * g.tiles_n;     // pair tiles of 256 rows
-    int64_t pairs = g.num_tiles < kNumSMs / 2 ? g.num_tiles : kNumSMs / 2;
-    tc_gemm_nt3_kernel<<<(unsigned)(2 * pairs), kV2Threads, smem, st>>>(g);
-    return check_launch("tc_gemm_nt3");
-}
-
 // ---- fp32 emulation with three fp16 MMAs (kind::f16) ----------------------------------------------------------------
 // x*s = hi + lo with hi = fp16(x*s), lo = fp16(x*s - hi): two round-to-nearest 11-bit pieces carry 22+ bits of x, so
 // hi*hi + hi*lo + lo*hi (fp32 accumulation in TMEM) has the accuracy of an fp32 product sum (measured: closer to the
@@ -1370,7 +1117,7 @@ static int launch_nt16(const Nt16Args& g, cudaStream_t st) {
     return check_launch("tc_gemm_nt16");
 }
 
-// fp16-split NT kernel on CTA pairs (cta_group::2, see tc_gemm_nt3_kernel for the synchronisation scheme): each CTA
+// fp16-split NT kernel on CTA pairs (cta_group::2, synchronisation scheme above): each CTA
 // stages its 128 rows of A and HALF of the weight tile, so the bytes a CTA pulls from L2 per k-block drop from 96 KB to
 // 64 KB (with the MMA time halved by kind::f16, the weight stream re-read for every row tile is what saturates the
 // SM's L2 port) and a third pipeline stage fits.
