@@ -193,7 +193,7 @@ colsum_finalize_kernel(const float* __restrict__ partials, int64_t nblk, int C, 
 // channels (cv) and every RL-th row, RL = 256/(C/4) when C/4 <= 256.  MODE 0: BN-backward reduce (2 sets),
 // MODE 1: BN-backward apply (+ 1 set: column sum of dY), MODE 2: plain column sum (1 set).
 // 5 CTAs per SM (<= 48 registers; the unconstrained build takes 56 / 60 and fits 4): the kernels are pure streams, more
-// rows in flight is all that counts -- 15.7 -> 14.9 ms per step at 1M faces (scripts/gpu_r2_m.sh; 6 CTAs = 40 registers
+// rows in flight is all that counts -- 15.7 -> 14.9 ms per step at 1M faces (scripts/records/gpu_r2_m.sh; 6 CTAs = 40 registers
 // spills in the loop).  One CTA also fits beside a resident tcgen05 GEMM CTA of the other network's stream.
 #ifndef DDMP_ROWBLOCK_MINB
 #define DDMP_ROWBLOCK_MINB 5
